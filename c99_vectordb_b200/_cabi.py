@@ -1,0 +1,89 @@
+"""ctypes binding of include/b200_flat.h (the C-ABI library c99_vectordb_b200/_b200flat.so).
+
+There is no fallback: if the library is missing it is built with nvcc; if that fails, or if a
+compute entry point reports an error (no CUDA device, wrong architecture …), a RuntimeError is
+raised.  Nothing here imports the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "_b200flat.so"
+
+METRIC_IP, METRIC_L2 = 0, 1
+STORE_F32, STORE_BF16 = 0, 1
+SCAN_AUTO, SCAN_BULK, SCAN_LDG = 0, 1, 2
+
+# every symbol include/b200_flat.h declares: (name, restype, argtypes)
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int64)
+_h = C.c_void_p
+SIGNATURES = [
+    ("b200_abi_version", C.c_int, []),
+    ("b200_last_error", C.c_char_p, []),
+    ("b200_device_count", C.c_int, [C.POINTER(C.c_int)]),
+    ("b200_index_create", C.c_int, [C.POINTER(_h), C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("b200_index_destroy", C.c_int, [_h]),
+    ("b200_index_reset", C.c_int, [_h]),
+    ("b200_index_reserve", C.c_int, [_h, C.c_int64]),
+    ("b200_index_set_option", C.c_int, [_h, C.c_char_p, C.c_int64]),
+    ("b200_index_get_option", C.c_int, [_h, C.c_char_p, _ip]),
+    ("b200_index_add", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    ("b200_index_add_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    ("b200_index_add_synthetic", C.c_int, [_h, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int64]),
+    ("b200_index_search", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    ("b200_index_search_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("b200_index_launch_count", C.c_int64, [_h]),
+    ("b200_index_sync", C.c_int, [_h]),
+    ("b200_index_ntotal", C.c_int64, [_h]),
+    ("b200_index_d", C.c_int, [_h]),
+    ("b200_index_metric", C.c_int, [_h]),
+    ("b200_index_store", C.c_int, [_h]),
+    ("b200_index_has_ids", C.c_int, [_h]),
+    ("b200_index_get_ids", C.c_int, [_h, C.c_void_p]),
+    ("b200_index_get_rows", C.c_int, [_h, C.c_int64, C.c_int64, C.c_void_p]),
+    ("b200_index_rows_dev", C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    ("b200_normalize_rows", C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int]),
+    ("b200_merge_topk_dev", C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("b200_synth_rows_dev", C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load (building first if absent) the native library; raise loudly if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        from . import build as _build
+
+        _build.build_cuda()
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"native library {LIB_PATH} is missing and could not be built (no CPU fallback exists)")
+    L = C.CDLL(str(LIB_PATH))
+    for name, restype, argtypes in SIGNATURES:
+        fn = getattr(L, name)  # AttributeError here == header/library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return load().b200_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    """Status -> exception.  faiss raises RuntimeError from C++ FaissException [upstream]."""
+    if rc != 0:
+        raise RuntimeError(last_error() or f"b200 native call failed with status {rc}")
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(load().b200_device_count(C.byref(n)))
+    return n.value

@@ -1,0 +1,57 @@
+"""Build the in-tree native library.
+
+  c99_vectordb_b200/_b200flat.so   the C-ABI library (include/b200_flat.h) — sm_100a CUDA
+
+nvcc cross-compiles without a GPU.  The CUDA runtime is linked statically so the library loads
+(and exports its symbols) on a box with no driver; compute entry points then fail loudly.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "c99_vectordb_b200" / "csrc"
+LIB = ROOT / "c99_vectordb_b200" / "_b200flat.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+    "--cudart", "static",
+]
+
+
+def _newer(target: Path, sources: list[Path]) -> bool:
+    if not target.exists():
+        return False
+    t = target.stat().st_mtime
+    return all(s.stat().st_mtime <= t for s in sources)
+
+
+def nvcc_path() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> Path:
+    sources = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "b200_flat.h"]
+    if not force and _newer(LIB, sources):
+        return LIB
+    cmd = [nvcc_path(), *NVCC_FLAGS]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", str(LIB)] + [str(s) for s in sorted(CSRC.glob("*.cu"))]
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    force = "--force" in sys.argv
+    verbose = "-v" in sys.argv
+    print(build_cuda(force, verbose))

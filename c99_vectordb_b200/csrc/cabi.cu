@@ -1,0 +1,831 @@
+// cabi.cu — the C ABI of include/b200_flat.h over the sm_100a kernels.
+// Single translation unit: nvcc -shared -gencode arch=compute_100a,code=sm_100a (see build.py).
+#include "../../include/b200_flat.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "fullrank.cuh"
+#include "merge.cuh"
+#include "rows.cuh"
+#include "scan_topk.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CKI(call)                \
+    do {                         \
+        int r_ = (call);         \
+        if (r_ != 0) return r_;  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+struct b200_index {
+    int d = 0, d_pad = 0, metric = 0, store = 0, device = 0;
+    size_t pitch = 0;  // bytes per stored row
+    uint8_t* rows = nullptr;
+    int64_t ntotal = 0, capacity = 0;
+    int64_t* ids = nullptr;
+    int64_t ids_capacity = 0;
+    int ids_state = 0;  // 0 undecided, 1 explicit ids, 2 ids == row positions
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    // scratch
+    uint64_t* partials = nullptr;
+    size_t partials_cap = 0;  // keys
+    unsigned int* ticket = nullptr;
+    float* q_dev = nullptr;   // staged host queries
+    float* qn_dev = nullptr;  // normalised queries
+    size_t q_cap = 0, qn_cap = 0;  // floats
+    float* D_dev = nullptr;
+    int64_t* I_dev = nullptr;
+    size_t out_cap = 0;  // entries
+    void* pin = nullptr;  // pinned staging for small searches
+    size_t pin_cap = 0;
+    float* stage = nullptr;  // device staging for ingest
+    size_t stage_cap = 0;    // bytes
+    uint32_t* fr_hi = nullptr;  // full-rank: [QB, n] hi keys
+    uint32_t* fr_buf[4] = {nullptr, nullptr, nullptr, nullptr};  // keys A/B, rows A/B
+    uint32_t* fr_hist = nullptr;
+    size_t fr_cap = 0, fr_hi_cap = 0, fr_hist_cap = 0;
+    // options
+    int64_t opt_variant = B200_SCAN_AUTO, opt_warps = 8, opt_stages = 0, opt_tile_rows = 0,
+            opt_ctas_per_sm = 0, opt_evict_first = 0, opt_fullrank_min_k = B200_FUSED_K_MAX + 1,
+            opt_normalize_queries = 0, opt_qb = 0;
+    int64_t launches = 0;
+};
+
+static int use_device(b200_index* ix) {
+    CK(cudaSetDevice(ix->device));
+    return 0;
+}
+
+template <typename T>
+static int grow(T** p, size_t* cap, size_t need) {
+    if (*cap >= need) return 0;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    CK(cudaMalloc((void**)p, need * sizeof(T)));
+    *cap = need;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------------------------
+extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
+extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
+extern "C" int b200_device_count(int* out_count) {
+    if (!out_count) return fail("out_count is null");
+    CK(cudaGetDeviceCount(out_count));
+    return 0;
+}
+
+extern "C" int b200_index_create(b200_index** out, int d, int metric, int store, int device) {
+    if (!out) return fail("out is null");
+    *out = nullptr;
+    if (d <= 0) return fail("d must be positive, got %d", d);
+    if (metric != B200_METRIC_IP && metric != B200_METRIC_L2) return fail("unknown metric %d", metric);
+    if (store != B200_STORE_F32 && store != B200_STORE_BF16) return fail("unknown store %d", store);
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (count <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= count) return fail("device %d out of range (have %d)", device, count);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    b200_index* ix = new b200_index();
+    ix->d = d;
+    ix->metric = metric;
+    ix->store = store;
+    ix->device = device;
+    ix->d_pad = store == B200_STORE_F32 ? (d + 3) / 4 * 4 : (d + 7) / 8 * 8;
+    ix->pitch = (size_t)ix->d_pad * (store == B200_STORE_F32 ? 4 : 2);
+    ix->num_sms = prop.multiProcessorCount;
+    ix->smem_optin = prop.sharedMemPerBlockOptin;
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ix->ticket, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(ix->ticket, 0, sizeof(unsigned int));
+    if (e != cudaSuccess) {
+        delete ix;
+        return fail("index create: %s", cudaGetErrorString(e));
+    }
+    *out = ix;
+    return 0;
+}
+
+extern "C" int b200_index_destroy(b200_index* ix) {
+    if (!ix) return 0;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    cudaFree(ix->rows);
+    cudaFree(ix->ids);
+    cudaFree(ix->partials);
+    cudaFree(ix->ticket);
+    cudaFree(ix->q_dev);
+    cudaFree(ix->qn_dev);
+    cudaFree(ix->D_dev);
+    cudaFree(ix->I_dev);
+    cudaFree(ix->stage);
+    cudaFree(ix->fr_hi);
+    for (int i = 0; i < 4; ++i) cudaFree(ix->fr_buf[i]);
+    cudaFree(ix->fr_hist);
+    if (ix->pin) cudaFreeHost(ix->pin);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+    return 0;
+}
+
+extern "C" int b200_index_reset(b200_index* ix) {
+    if (!ix) return fail("null index");
+    CKI(use_device(ix));
+    CK(cudaStreamSynchronize(ix->stream));
+    ix->ntotal = 0;
+    ix->ids_state = 0;
+    return 0;
+}
+
+static int ensure_capacity(b200_index* ix, int64_t need, bool need_ids) {
+    if (need > 0xFFFFFFF0ll) return fail("at most 2^32-16 rows per index shard, asked for %lld", (long long)need);
+    if (need > ix->capacity) {
+        int64_t cap = std::max<int64_t>(need, std::max<int64_t>(1024, ix->capacity + ix->capacity / 2));
+        uint8_t* nr = nullptr;
+        cudaError_t e = cudaMalloc((void**)&nr, (size_t)cap * ix->pitch);
+        if (e != cudaSuccess && cap > need) {  // retry with the exact size
+            cudaGetLastError();
+            cap = need;
+            e = cudaMalloc((void**)&nr, (size_t)cap * ix->pitch);
+        }
+        if (e != cudaSuccess)
+            return fail("cannot allocate %.2f GB of row storage: %s", (double)cap * ix->pitch / 1e9,
+                        cudaGetErrorString(e));
+        if (ix->ntotal > 0)
+            CK(cudaMemcpyAsync(nr, ix->rows, (size_t)ix->ntotal * ix->pitch, cudaMemcpyDeviceToDevice, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+        if (ix->rows) CK(cudaFree(ix->rows));
+        ix->rows = nr;
+        ix->capacity = cap;
+    }
+    if (need_ids && need > ix->ids_capacity) {
+        int64_t cap = std::max<int64_t>(need, ix->capacity);
+        int64_t* ni = nullptr;
+        CK(cudaMalloc((void**)&ni, (size_t)cap * sizeof(int64_t)));
+        if (ix->ntotal > 0 && ix->ids)
+            CK(cudaMemcpyAsync(ni, ix->ids, (size_t)ix->ntotal * sizeof(int64_t), cudaMemcpyDeviceToDevice, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+        if (ix->ids) CK(cudaFree(ix->ids));
+        ix->ids = ni;
+        ix->ids_capacity = cap;
+    }
+    return 0;
+}
+
+extern "C" int b200_index_reserve(b200_index* ix, int64_t n_total) {
+    if (!ix) return fail("null index");
+    CKI(use_device(ix));
+    return ensure_capacity(ix, n_total, ix->ids_state == 1);
+}
+
+struct OptName {
+    const char* name;
+    int64_t b200_index::*field;
+};
+static const OptName kOpts[] = {
+    {"scan_variant", &b200_index::opt_variant},
+    {"scan_warps", &b200_index::opt_warps},
+    {"scan_stages", &b200_index::opt_stages},
+    {"scan_tile_rows", &b200_index::opt_tile_rows},
+    {"scan_ctas_per_sm", &b200_index::opt_ctas_per_sm},
+    {"scan_l2_evict_first", &b200_index::opt_evict_first},
+    {"scan_query_block", &b200_index::opt_qb},
+    {"fullrank_min_k", &b200_index::opt_fullrank_min_k},
+    {"normalize_queries", &b200_index::opt_normalize_queries},
+};
+extern "C" int b200_index_set_option(b200_index* ix, const char* name, int64_t value) {
+    if (!ix || !name) return fail("null argument");
+    for (const OptName& o : kOpts)
+        if (strcmp(o.name, name) == 0) {
+            ix->*(o.field) = value;
+            return 0;
+        }
+    return fail("unknown option '%s'", name);
+}
+extern "C" int b200_index_get_option(b200_index* ix, const char* name, int64_t* out_value) {
+    if (!ix || !name || !out_value) return fail("null argument");
+    for (const OptName& o : kOpts)
+        if (strcmp(o.name, name) == 0) {
+            *out_value = ix->*(o.field);
+            return 0;
+        }
+    return fail("unknown option '%s'", name);
+}
+
+// ---------------------------------------------------------------------------------------------
+// add
+// ---------------------------------------------------------------------------------------------
+typedef void (*IngestFn)(const IngestParams);
+static IngestFn pick_ingest(int store, int normalize, int vec) {
+#define ING(S, N, V) \
+    if (store == S && normalize == N && vec == V) return ingest_rows_kernel<S, N, V>;
+    ING(0, 0, 0) ING(0, 0, 1) ING(0, 1, 0) ING(0, 1, 1) ING(1, 0, 0) ING(1, 0, 1) ING(1, 1, 0) ING(1, 1, 1)
+#undef ING
+    return nullptr;
+}
+
+static int ingest_dev(int d, int d_pad, int store, const float* src_dev, uint8_t* dst, size_t dst_pitch,
+                      int64_t n, int normalize, int num_sms, cudaStream_t st, int64_t* launches) {
+    if (n <= 0) return 0;
+    IngestParams p;
+    p.src = src_dev;
+    p.dst = dst;
+    p.pitch_bytes = dst_pitch;
+    p.n = (uint64_t)n;
+    p.d = d;
+    p.d_pad = d_pad;
+    int vec = (d % 4 == 0) && (((uintptr_t)src_dev & 15) == 0);
+    IngestFn fn = pick_ingest(store, normalize ? 1 : 0, vec);
+    int64_t blocks = std::min<int64_t>((n + 7) / 8, (int64_t)num_sms * 8);
+    fn<<<(unsigned)std::max<int64_t>(1, blocks), 256, 0, st>>>(p);
+    if (launches) ++*launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int note_ids(b200_index* ix, bool explicit_ids) {
+    int want = explicit_ids ? 1 : 2;
+    if (ix->ntotal > 0 && ix->ids_state != 0 && ix->ids_state != want)
+        return fail("cannot mix add() and add_with_ids() on one index");
+    ix->ids_state = want;
+    return 0;
+}
+
+static int add_common(b200_index* ix, const float* x, bool x_is_dev, int64_t n, const int64_t* ids,
+                      int normalize) {
+    if (!ix) return fail("null index");
+    if (n < 0) return fail("negative n");
+    if (n == 0) return 0;
+    if (!x) return fail("x is null");
+    CKI(use_device(ix));
+    CKI(note_ids(ix, ids != nullptr));
+    CKI(ensure_capacity(ix, ix->ntotal + n, ids != nullptr));
+    cudaStream_t st = ix->stream;
+    if (ids)
+        CK(cudaMemcpyAsync(ix->ids + ix->ntotal, ids, (size_t)n * sizeof(int64_t),
+                           x_is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    uint8_t* dst = ix->rows + (size_t)ix->ntotal * ix->pitch;
+    const bool plain = (ix->store == B200_STORE_F32) && !normalize && (ix->d == ix->d_pad);
+    if (plain) {
+        CK(cudaMemcpyAsync(dst, x, (size_t)n * ix->pitch,
+                           x_is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    } else if (x_is_dev) {
+        CKI(ingest_dev(ix->d, ix->d_pad, ix->store, x, dst, ix->pitch, n, normalize, ix->num_sms, st, &ix->launches));
+    } else {
+        // host rows: stage through a device buffer in chunks, K1 writes the resident rows
+        const size_t row_bytes = (size_t)ix->d * 4;
+        size_t chunk_rows = std::max<size_t>(1, ((size_t)256 << 20) / row_bytes);
+        chunk_rows = std::min<size_t>(chunk_rows, (size_t)n);
+        if (ix->stage_cap < chunk_rows * row_bytes) {
+            if (ix->stage) CK(cudaFree(ix->stage));
+            ix->stage = nullptr;
+            ix->stage_cap = 0;
+            CK(cudaMalloc((void**)&ix->stage, chunk_rows * row_bytes));
+            ix->stage_cap = chunk_rows * row_bytes;
+        }
+        for (int64_t r0 = 0; r0 < n; r0 += (int64_t)chunk_rows) {
+            int64_t nr = std::min<int64_t>((int64_t)chunk_rows, n - r0);
+            CK(cudaMemcpyAsync(ix->stage, x + (size_t)r0 * ix->d, (size_t)nr * row_bytes, cudaMemcpyHostToDevice, st));
+            CKI(ingest_dev(ix->d, ix->d_pad, ix->store, ix->stage, dst + (size_t)r0 * ix->pitch, ix->pitch, nr,
+                           normalize, ix->num_sms, st, &ix->launches));
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    ix->ntotal += n;
+    return 0;
+}
+
+extern "C" int b200_index_add(b200_index* ix, const float* x_host, int64_t n, const int64_t* ids_host,
+                              int normalize) {
+    return add_common(ix, x_host, false, n, ids_host, normalize);
+}
+extern "C" int b200_index_add_dev(b200_index* ix, const float* x_dev, int64_t n, const int64_t* ids_dev,
+                                  int normalize) {
+    return add_common(ix, x_dev, true, n, ids_dev, normalize);
+}
+
+extern "C" int b200_synth_rows_dev(float* out_dev, int64_t n, int d, uint64_t seed, int64_t first_row,
+                                   int normalize, void* stream) {
+    if (!out_dev || n < 0 || d <= 0) return fail("bad argument");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    synth_rows_kernel<<<sms * 8, 256, 0, st>>>(out_dev, (uint64_t)n, (uint32_t)d, seed, (uint64_t)first_row);
+    CK(cudaGetLastError());
+    if (normalize) {
+        // in place: same pitch as the dense source when d % 4 == 0
+        if (d % 4 != 0) return fail("in-place synthetic normalisation needs d %% 4 == 0");
+        CKI(ingest_dev(d, d, B200_STORE_F32, out_dev, (uint8_t*)out_dev, (size_t)d * 4, n, 1, sms, st, nullptr));
+    }
+    return 0;
+}
+
+extern "C" int b200_index_add_synthetic(b200_index* ix, int64_t n, uint64_t seed, int64_t first_row,
+                                        int normalize, int with_ids, int64_t first_id) {
+    if (!ix) return fail("null index");
+    if (n < 0) return fail("negative n");
+    if (n == 0) return 0;
+    CKI(use_device(ix));
+    CKI(note_ids(ix, with_ids != 0));
+    CKI(ensure_capacity(ix, ix->ntotal + n, with_ids != 0));
+    cudaStream_t st = ix->stream;
+    const size_t row_bytes = (size_t)ix->d * 4;
+    size_t chunk_rows = std::max<size_t>(1, ((size_t)256 << 20) / row_bytes);
+    chunk_rows = std::min<size_t>(chunk_rows, (size_t)n);
+    if (ix->stage_cap < chunk_rows * row_bytes) {
+        if (ix->stage) CK(cudaFree(ix->stage));
+        ix->stage = nullptr;
+        ix->stage_cap = 0;
+        CK(cudaMalloc((void**)&ix->stage, chunk_rows * row_bytes));
+        ix->stage_cap = chunk_rows * row_bytes;
+    }
+    uint8_t* dst = ix->rows + (size_t)ix->ntotal * ix->pitch;
+    for (int64_t r0 = 0; r0 < n; r0 += (int64_t)chunk_rows) {
+        int64_t nr = std::min<int64_t>((int64_t)chunk_rows, n - r0);
+        synth_rows_kernel<<<ix->num_sms * 8, 256, 0, st>>>(ix->stage, (uint64_t)nr, (uint32_t)ix->d, seed,
+                                                           (uint64_t)(first_row + r0));
+        ++ix->launches;
+        CK(cudaGetLastError());
+        CKI(ingest_dev(ix->d, ix->d_pad, ix->store, ix->stage, dst + (size_t)r0 * ix->pitch, ix->pitch, nr,
+                       normalize, ix->num_sms, st, &ix->launches));
+    }
+    if (with_ids) {
+        iota_ids_kernel<<<ix->num_sms * 4, 256, 0, st>>>(ix->ids + ix->ntotal, (uint64_t)n, first_id);
+        ++ix->launches;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(st));
+    ix->ntotal += n;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------
+struct ScanPlan {
+    int variant = 0, nw = 0, qb = 0;
+    uint32_t tile_rows = 0, stages = 0, tile_bytes = 0, scratch_keys = 0;
+    size_t smem = 0;
+    int grid = 0;
+};
+
+typedef void (*ScanFn)(const ScanParams);
+#define SCAN_RB 4
+static ScanFn pick_scan(int metric, int store, int qb, int variant) {
+#define SC(M, S, Q, V) \
+    if (metric == M && store == S && qb == Q && variant == V) return scan_topk_kernel<M, S, Q, SCAN_RB, V>;
+#define SC_Q(M, S, V) SC(M, S, 1, V) SC(M, S, 2, V) SC(M, S, 4, V) SC(M, S, 8, V)
+#define SC_S(M, V) SC_Q(M, 0, V) SC_Q(M, 1, V)
+    SC_S(0, B200_VARIANT_BULK) SC_S(1, B200_VARIANT_BULK) SC_S(0, B200_VARIANT_LDG) SC_S(1, B200_VARIANT_LDG)
+#undef SC_S
+#undef SC_Q
+#undef SC
+    return nullptr;
+}
+
+static uint32_t next_pow2(uint32_t v) {
+    uint32_t m = 1;
+    while (m < v) m <<= 1;
+    return m;
+}
+
+static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out) {
+    ScanPlan pl;
+    pl.qb = qb;
+    const int qstride = (ix->d_pad + 7) / 8 * 8;
+    const int kk = fullrank ? 1 : k;
+    const size_t budget = ix->smem_optin - 1024;
+    int variant = (int)ix->opt_variant;
+    if (variant == B200_SCAN_AUTO) variant = B200_VARIANT_BULK;
+    if (variant == B200_VARIANT_BULK) {
+        int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_MAX / 32);
+        bool ok = false;
+        for (; nw >= 1; nw >>= 1) {
+            uint32_t tr;
+            if (ix->opt_tile_rows > 0)
+                tr = (uint32_t)((ix->opt_tile_rows + SCAN_RB - 1) / SCAN_RB * SCAN_RB);
+            else {
+                double groups = 12288.0 / ((double)SCAN_RB * ix->pitch);
+                uint32_t m = (uint32_t)std::max(1.0, groups + 0.5);
+                tr = m * SCAN_RB;
+            }
+            uint64_t tile_bytes = (uint64_t)tr * ix->pitch;
+            if (tile_bytes > (1u << 19)) break;  // mbarrier tx-count headroom
+            uint32_t scratch = std::max<uint32_t>(B200_FINAL_BUF_KEYS, next_pow2((uint32_t)(nw * kk)));
+            size_t fixed = scan_smem_bytes(B200_VARIANT_BULK, nw, qb, qstride, kk, fullrank, 0, 0, scratch);
+            // ring replaces the scratch region when larger
+            size_t fixed_wo_scratch = fixed - (((size_t)scratch * 8 + 127) & ~(size_t)127);
+            if (fixed_wo_scratch + 64 >= budget) continue;
+            size_t avail = budget - fixed_wo_scratch - 64;
+            uint32_t stages = (uint32_t)std::min<uint64_t>(8, avail / ((uint64_t)nw * tile_bytes + (uint64_t)nw * 8));
+            if (ix->opt_stages > 0) stages = std::min<uint32_t>(stages, (uint32_t)ix->opt_stages);
+            if (stages < 2) continue;
+            size_t smem = scan_smem_bytes(B200_VARIANT_BULK, nw, qb, qstride, kk, fullrank, stages, (uint32_t)tile_bytes, scratch);
+            if (smem > budget) continue;
+            pl.variant = B200_VARIANT_BULK;
+            pl.nw = nw;
+            pl.tile_rows = tr;
+            pl.stages = stages;
+            pl.tile_bytes = (uint32_t)tile_bytes;
+            pl.scratch_keys = scratch;
+            pl.smem = smem;
+            pl.grid = ix->num_sms;  // one persistent CTA per SM
+            ok = true;
+            break;
+        }
+        if (!ok) variant = B200_VARIANT_LDG;
+    }
+    if (variant == B200_VARIANT_LDG) {
+        int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_MAX / 32);
+        for (;; nw >>= 1) {
+            if (nw < 1) return fail("k=%d does not fit the fused top-k shared-memory budget", k);
+            uint32_t scratch = std::max<uint32_t>(B200_FINAL_BUF_KEYS, next_pow2((uint32_t)(nw * kk)));
+            size_t smem = scan_smem_bytes(B200_VARIANT_LDG, nw, qb, qstride, kk, fullrank, 0, 0, scratch);
+            if (smem > budget) continue;
+            pl.variant = B200_VARIANT_LDG;
+            pl.nw = nw;
+            pl.tile_rows = SCAN_RB;
+            pl.stages = 0;
+            pl.tile_bytes = 0;
+            pl.scratch_keys = scratch;
+            pl.smem = smem;
+            break;
+        }
+        ScanFn fn = pick_scan(ix->metric, ix->store, qb, B200_VARIANT_LDG);
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl.nw * 32, pl.smem));
+        if (occ < 1) return fail("LDG scan kernel does not fit on an SM (smem %zu)", pl.smem);
+        if (ix->opt_ctas_per_sm > 0) occ = (int)std::min<int64_t>(occ, ix->opt_ctas_per_sm);
+        pl.grid = occ * ix->num_sms;
+    }
+    *out = pl;
+    return 0;
+}
+
+template <int METRIC>
+__global__ void fill_pad_kernel(float* D, int64_t* I, int64_t count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        D[i] = METRIC == 0 ? -FLT_MAX : FLT_MAX;
+        I[i] = -1;
+    }
+}
+
+static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, int nqb, int k, float* D,
+                       int64_t* I, uint32_t* score_keys, cudaStream_t st) {
+    ScanParams p;
+    memset(&p, 0, sizeof p);
+    p.rows = ix->rows;
+    p.pitch_bytes = ix->pitch;
+    p.nvec = (uint32_t)(ix->pitch / 16);
+    p.n = (uint64_t)ix->ntotal;
+    p.q = q_dev;
+    p.d = ix->d;
+    p.qstride = (ix->d_pad + 7) / 8 * 8;
+    p.nqb = nqb;
+    p.k = score_keys ? 1 : k;
+    p.ticket = ix->ticket;
+    p.D = D;
+    p.I = I;
+    p.id_map = ix->ids_state == 1 ? ix->ids : nullptr;
+    p.id_base = 0;
+    p.tile_rows = pl.tile_rows;
+    p.stages = pl.stages;
+    p.tile_bytes = pl.tile_bytes;
+    p.evict_first = (int)ix->opt_evict_first;
+    p.score_keys = score_keys;
+    p.scratch_keys = pl.scratch_keys;
+    if (!score_keys) {
+        size_t need = (size_t)pl.grid * pl.qb * k;
+        CKI(grow(&ix->partials, &ix->partials_cap, need));
+    }
+    p.partials = ix->partials;
+    ScanFn fn = pick_scan(ix->metric, ix->store, pl.qb, pl.variant);
+    if (!fn) return fail("no scan kernel for metric=%d store=%d qb=%d variant=%d", ix->metric, ix->store, pl.qb, pl.variant);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    fn<<<pl.grid, pl.nw * 32, pl.smem, st>>>(p);
+    ++ix->launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int fullrank_one(b200_index* ix, const uint32_t* hi_keys, int64_t k, float* D, int64_t* I, cudaStream_t st) {
+    const uint64_t n = (uint64_t)ix->ntotal;
+    const uint32_t nblocks = (uint32_t)((n + RADIX_CHUNK - 1) / RADIX_CHUNK);
+    if (ix->fr_cap < n) {
+        for (int i = 0; i < 4; ++i) {
+            if (ix->fr_buf[i]) CK(cudaFree(ix->fr_buf[i]));
+            ix->fr_buf[i] = nullptr;
+        }
+        ix->fr_cap = 0;
+        for (int i = 0; i < 4; ++i) CK(cudaMalloc((void**)&ix->fr_buf[i], n * sizeof(uint32_t)));
+        ix->fr_cap = n;
+    }
+    CKI(grow(&ix->fr_hist, &ix->fr_hist_cap, (size_t)256 * nblocks));
+    uint32_t *ka = ix->fr_buf[0], *kb = ix->fr_buf[1], *va = ix->fr_buf[2], *vb = ix->fr_buf[3];
+    fullrank_prepare_kernel<<<ix->num_sms * 4, 256, 0, st>>>(hi_keys, ka, va, n);
+    ++ix->launches;
+    for (int pass = 0; pass < 4; ++pass) {
+        int shift = 8 * pass;
+        radix_hist_kernel<<<nblocks, RADIX_THREADS, 0, st>>>(ka, n, shift, ix->fr_hist, nblocks);
+        radix_scan_kernel<<<1, 1024, 0, st>>>(ix->fr_hist, (uint64_t)256 * nblocks);
+        radix_scatter_kernel<<<nblocks, RADIX_THREADS, 0, st>>>(ka, va, kb, vb, n, shift, ix->fr_hist, nblocks);
+        ix->launches += 3;
+        std::swap(ka, kb);
+        std::swap(va, vb);
+    }
+    const int64_t* idm = ix->ids_state == 1 ? ix->ids : nullptr;
+    unsigned eb = (unsigned)std::min<int64_t>((k + 255) / 256, (int64_t)ix->num_sms * 8);
+    if (ix->metric == B200_METRIC_IP)
+        fullrank_emit_kernel<0><<<eb, 256, 0, st>>>(ka, va, n, k, idm, 0, D, I);
+    else
+        fullrank_emit_kernel<1><<<eb, 256, 0, st>>>(ka, va, n, k, idm, 0, D, I);
+    ++ix->launches;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int pick_qb(int64_t remaining, int64_t forced) {
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return (int)forced;
+    if (remaining >= 8) return 8;
+    if (remaining > 2) return 4;
+    if (remaining == 2) return 2;
+    return 1;
+}
+
+extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev,
+                                     int64_t* I_dev, void* stream) {
+    if (!ix) return fail("null index");
+    if (nq < 0) return fail("negative nq");
+    if (k <= 0) return fail("k must be positive, got %lld", (long long)k);
+    if (nq == 0) return 0;
+    if (!q_dev || !D_dev || !I_dev) return fail("null buffer");
+    if (nq * k > ((int64_t)1 << 40)) return fail("result too large");
+    CKI(use_device(ix));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    if (ix->ntotal == 0) {
+        int64_t count = nq * k;
+        unsigned blocks = (unsigned)((count + 255) / 256);
+        if (ix->metric == B200_METRIC_IP)
+            fill_pad_kernel<0><<<blocks, 256, 0, st>>>(D_dev, I_dev, count);
+        else
+            fill_pad_kernel<1><<<blocks, 256, 0, st>>>(D_dev, I_dev, count);
+        ++ix->launches;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    if (ix->opt_normalize_queries) {
+        if (ix->qn_cap < (size_t)nq * ix->d) {
+            CK(cudaStreamSynchronize(st));
+            CKI(grow(&ix->qn_dev, &ix->qn_cap, (size_t)nq * ix->d));
+        }
+        if (ix->d % 4 != 0) return fail("normalize_queries needs d %% 4 == 0");
+        CKI(ingest_dev(ix->d, ix->d, B200_STORE_F32, q_dev, (uint8_t*)ix->qn_dev, (size_t)ix->d * 4, nq, 1,
+                       ix->num_sms, st, &ix->launches));
+        q_dev = ix->qn_dev;
+    }
+    const bool fullrank = k >= ix->opt_fullrank_min_k || k > B200_FUSED_K_MAX;
+    if (!fullrank) {
+        int64_t q0 = 0;
+        while (q0 < nq) {
+            int qb = pick_qb(nq - q0, ix->opt_qb);
+            int nqb = (int)std::min<int64_t>(qb, nq - q0);
+            ScanPlan pl;
+            CKI(plan_scan(ix, qb, (int)k, false, &pl));
+            CKI(launch_scan(ix, pl, q_dev + (size_t)q0 * ix->d, nqb, (int)k, D_dev + (size_t)q0 * k,
+                            I_dev + (size_t)q0 * k, nullptr, st));
+            q0 += nqb;
+        }
+        return 0;
+    }
+    // full ranking: scores for a block of queries, then one stable radix sort per query
+    const uint64_t n = (uint64_t)ix->ntotal;
+    int64_t q0 = 0;
+    while (q0 < nq) {
+        int qb = pick_qb(nq - q0, ix->opt_qb);
+        int nqb = (int)std::min<int64_t>(qb, nq - q0);
+        if (ix->fr_hi_cap < (size_t)qb * n) {
+            CK(cudaStreamSynchronize(st));
+            CKI(grow(&ix->fr_hi, &ix->fr_hi_cap, (size_t)qb * n));
+        }
+        ScanPlan pl;
+        CKI(plan_scan(ix, qb, 1, true, &pl));
+        CKI(launch_scan(ix, pl, q_dev + (size_t)q0 * ix->d, nqb, 1, nullptr, nullptr, ix->fr_hi, st));
+        for (int qi = 0; qi < nqb; ++qi)
+            CKI(fullrank_one(ix, ix->fr_hi + (size_t)qi * n, k, D_dev + (size_t)(q0 + qi) * k,
+                             I_dev + (size_t)(q0 + qi) * k, st));
+        q0 += nqb;
+    }
+    return 0;
+}
+
+extern "C" int b200_index_search(b200_index* ix, const float* q_host, int64_t nq, int64_t k, float* D_host,
+                                 int64_t* I_host) {
+    if (!ix) return fail("null index");
+    if (nq < 0) return fail("negative nq");
+    if (k <= 0) return fail("k must be positive, got %lld", (long long)k);
+    if (nq == 0) return 0;
+    if (!q_host || !D_host || !I_host) return fail("null buffer");
+    CKI(use_device(ix));
+    cudaStream_t st = ix->stream;
+    const size_t qn = (size_t)nq * ix->d, on = (size_t)nq * (size_t)k;
+    if (ix->q_cap < qn || ix->out_cap < on) CK(cudaStreamSynchronize(st));
+    CKI(grow(&ix->q_dev, &ix->q_cap, qn));
+    if (ix->out_cap < on) {
+        if (ix->D_dev) CK(cudaFree(ix->D_dev));
+        if (ix->I_dev) CK(cudaFree(ix->I_dev));
+        ix->D_dev = nullptr;
+        ix->I_dev = nullptr;
+        ix->out_cap = 0;
+        CK(cudaMalloc((void**)&ix->D_dev, on * sizeof(float)));
+        CK(cudaMalloc((void**)&ix->I_dev, on * sizeof(int64_t)));
+        ix->out_cap = on;
+    }
+    // small transfers go through pinned staging so the copies are truly asynchronous DMA
+    const size_t pin_need = qn * 4 + on * 12 + 64;
+    const bool use_pin = pin_need <= ((size_t)8 << 20);
+    if (use_pin && ix->pin_cap < pin_need) {
+        if (ix->pin) CK(cudaFreeHost(ix->pin));
+        ix->pin = nullptr;
+        ix->pin_cap = 0;
+        size_t cap = std::max<size_t>(pin_need, (size_t)1 << 16);
+        CK(cudaHostAlloc(&ix->pin, cap, cudaHostAllocDefault));
+        ix->pin_cap = cap;
+    }
+    if (use_pin) {
+        uint8_t* base = (uint8_t*)ix->pin;
+        int64_t* pI = (int64_t*)base;                       // 8-byte aligned first
+        float* pD = (float*)(base + on * 8);
+        float* pq = (float*)(base + on * 12);
+        memcpy(pq, q_host, qn * 4);
+        CK(cudaMemcpyAsync(ix->q_dev, pq, qn * 4, cudaMemcpyHostToDevice, st));
+        CKI(b200_index_search_dev(ix, ix->q_dev, nq, k, ix->D_dev, ix->I_dev, st));
+        CK(cudaMemcpyAsync(pD, ix->D_dev, on * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(pI, ix->I_dev, on * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(D_host, pD, on * 4);
+        memcpy(I_host, pI, on * 8);
+    } else {
+        CK(cudaMemcpyAsync(ix->q_dev, q_host, qn * 4, cudaMemcpyHostToDevice, st));
+        CKI(b200_index_search_dev(ix, ix->q_dev, nq, k, ix->D_dev, ix->I_dev, st));
+        CK(cudaMemcpyAsync(D_host, ix->D_dev, on * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(I_host, ix->I_dev, on * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+extern "C" int64_t b200_index_launch_count(b200_index* ix) { return ix ? ix->launches : -1; }
+extern "C" int b200_index_sync(b200_index* ix) {
+    if (!ix) return fail("null index");
+    CKI(use_device(ix));
+    CK(cudaStreamSynchronize(ix->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t b200_index_ntotal(b200_index* ix) { return ix ? ix->ntotal : -1; }
+extern "C" int b200_index_d(b200_index* ix) { return ix ? ix->d : -1; }
+extern "C" int b200_index_metric(b200_index* ix) { return ix ? ix->metric : -1; }
+extern "C" int b200_index_store(b200_index* ix) { return ix ? ix->store : -1; }
+extern "C" int b200_index_has_ids(b200_index* ix) { return ix ? (ix->ids_state == 1) : -1; }
+
+extern "C" int b200_index_get_ids(b200_index* ix, int64_t* out_host) {
+    if (!ix) return fail("null index");
+    if (ix->ntotal == 0) return 0;
+    if (!out_host) return fail("null buffer");
+    CKI(use_device(ix));
+    if (ix->ids_state == 1) {
+        CK(cudaMemcpyAsync(out_host, ix->ids, (size_t)ix->ntotal * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+    } else {
+        for (int64_t i = 0; i < ix->ntotal; ++i) out_host[i] = i;
+    }
+    return 0;
+}
+
+extern "C" int b200_index_get_rows(b200_index* ix, int64_t row0, int64_t n, float* out_host) {
+    if (!ix) return fail("null index");
+    if (row0 < 0 || n < 0 || row0 + n > ix->ntotal) return fail("row range [%lld,+%lld) out of bounds", (long long)row0, (long long)n);
+    if (n == 0) return 0;
+    if (!out_host) return fail("null buffer");
+    CKI(use_device(ix));
+    const uint8_t* src = ix->rows + (size_t)row0 * ix->pitch;
+    if (ix->store == B200_STORE_F32) {
+        CK(cudaMemcpy2DAsync(out_host, (size_t)ix->d * 4, src, ix->pitch, (size_t)ix->d * 4, (size_t)n,
+                             cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+    } else {
+        std::vector<uint16_t> tmp((size_t)n * ix->d_pad);
+        CK(cudaMemcpyAsync(tmp.data(), src, (size_t)n * ix->pitch, cudaMemcpyDeviceToHost, ix->stream));
+        CK(cudaStreamSynchronize(ix->stream));
+        for (int64_t r = 0; r < n; ++r)
+            for (int c = 0; c < ix->d; ++c) {
+                uint32_t u = (uint32_t)tmp[(size_t)r * ix->d_pad + c] << 16;
+                memcpy(&out_host[(size_t)r * ix->d + c], &u, 4);
+            }
+    }
+    return 0;
+}
+
+extern "C" int b200_index_rows_dev(b200_index* ix, void** out_ptr, size_t* out_pitch_bytes) {
+    if (!ix || !out_ptr || !out_pitch_bytes) return fail("null argument");
+    *out_ptr = ix->rows;
+    *out_pitch_bytes = ix->pitch;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone stages
+// ---------------------------------------------------------------------------------------------
+extern "C" int b200_normalize_rows(float* x_host, int64_t n, int d, int device) {
+    if (n < 0 || d <= 0) return fail("bad shape");
+    if (n == 0) return 0;
+    if (!x_host) return fail("null buffer");
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    if (count <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    CK(cudaSetDevice(device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int d_pad = (d + 3) / 4 * 4;
+    float *src = nullptr, *dst = nullptr;
+    CK(cudaMalloc((void**)&src, (size_t)n * d * 4));
+    cudaError_t e = cudaMalloc((void**)&dst, (size_t)n * d_pad * 4);
+    if (e != cudaSuccess) {
+        cudaFree(src);
+        return fail("cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    int rc = 0;
+    do {
+        if ((e = cudaMemcpy(src, x_host, (size_t)n * d * 4, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        rc = ingest_dev(d, d_pad, B200_STORE_F32, src, (uint8_t*)dst, (size_t)d_pad * 4, n, 1, sms, 0, nullptr);
+        if (rc) break;
+        e = cudaMemcpy2D(x_host, (size_t)d * 4, dst, (size_t)d_pad * 4, (size_t)d * 4, (size_t)n, cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(src);
+    cudaFree(dst);
+    if (e != cudaSuccess) return fail("normalize_rows: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+extern "C" int b200_merge_topk_dev(int metric, int G, int64_t nq, int64_t k, const float* D_parts_dev,
+                                   const int64_t* I_parts_dev, float* D_out_dev, int64_t* I_out_dev, void* stream) {
+    if (G <= 0 || nq < 0 || k <= 0) return fail("bad shape");
+    if (nq == 0) return 0;
+    if (!D_parts_dev || !I_parts_dev || !D_out_dev || !I_out_dev) return fail("null buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t total = (int64_t)G * nq * k;
+    unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    if (metric == B200_METRIC_IP)
+        merge_topk_kernel<0><<<blocks, 256, 0, st>>>(G, nq, k, D_parts_dev, I_parts_dev, D_out_dev, I_out_dev);
+    else if (metric == B200_METRIC_L2)
+        merge_topk_kernel<1><<<blocks, 256, 0, st>>>(G, nq, k, D_parts_dev, I_parts_dev, D_out_dev, I_out_dev);
+    else
+        return fail("unknown metric %d", metric);
+    CK(cudaGetLastError());
+    return 0;
+}

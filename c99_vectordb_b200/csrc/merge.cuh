@@ -1,0 +1,60 @@
+// merge.cuh — K4: merge G per-shard best-first result lists into one (multi-GPU top-k merge,
+// runs after the NCCL gather).  Replaces faiss's per-shard heap merge [upstream IndexShards /
+// HeapArray merge]; there is no analogue in memo_cli.py (single process).
+//
+// Rank-by-counting merge: every candidate (g,j) computes its final rank as the number of
+// candidates that precede it under (score best-first, lower shard first, earlier position first)
+// with one binary search per shard list, and writes itself to out[rank] if rank < k.  Ranks are a
+// permutation of 0..G*k-1, so every output slot is written exactly once — no shared memory, any k.
+#pragma once
+#include "common.cuh"
+
+template <int METRIC>
+__device__ __forceinline__ uint32_t merge_hi(float s, int64_t id) {
+    return (id < 0) ? 0u : b200_key_hi<METRIC>(s);
+}
+
+// lists are descending in hi.  number of entries with hi > h (strict) or hi >= h
+template <int METRIC>
+__device__ __forceinline__ int64_t count_better(const float* D, const int64_t* I, int64_t k,
+                                                uint32_t h, bool or_equal) {
+    int64_t lo = 0, hi = k;  // first index where the predicate fails
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        uint32_t hm = merge_hi<METRIC>(D[mid], I[mid]);
+        bool pred = or_equal ? (hm >= h) : (hm > h);
+        if (pred) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(int G, int64_t nq, int64_t k, const float* __restrict__ Dp,
+                  const int64_t* __restrict__ Ip, float* __restrict__ Do, int64_t* __restrict__ Io) {
+    const int64_t total = (int64_t)G * nq * k;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        // t enumerates (q, g, j)
+        int64_t q = t / (G * k);
+        int64_t r = t - q * (G * k);
+        int g = (int)(r / k);
+        int64_t j = r - (int64_t)g * k;
+        const float* Dme = Dp + ((int64_t)g * nq + q) * k;
+        const int64_t* Ime = Ip + ((int64_t)g * nq + q) * k;
+        float s = Dme[j];
+        int64_t id = Ime[j];
+        uint32_t h = merge_hi<METRIC>(s, id);
+        int64_t rank = j;
+        for (int g2 = 0; g2 < G; ++g2) {
+            if (g2 == g) continue;
+            const float* D2 = Dp + ((int64_t)g2 * nq + q) * k;
+            const int64_t* I2 = Ip + ((int64_t)g2 * nq + q) * k;
+            rank += count_better<METRIC>(D2, I2, k, h, /*or_equal=*/g2 < g);
+        }
+        if (rank < k) {
+            Do[q * k + rank] = (id < 0) ? ((METRIC == 0) ? -FLT_MAX : FLT_MAX) : s;
+            Io[q * k + rank] = (id < 0) ? (int64_t)-1 : id;
+        }
+    }
+}

@@ -1,0 +1,103 @@
+// rows.cuh — K1: row ingest at add time (optional L2 normalisation, optional fp32 -> bf16 store),
+// and the counter-based synthetic row generator.
+//
+// K1 replaces memo's normalize() (memo_cli.py:131-135): n = sqrt(sum v^2) in fp32; n <= 1e-8 ->
+// zero row; else v / n with a true (correctly rounded) division.  One warp per row; lane l owns
+// the 4-element chunks l, l+32, ... and sums squares in ascending element order with fmaf, then a
+// 16/8/4/2/1 xor butterfly (oracle/flat_oracle.c: oracle_normalize_device_order).
+#pragma once
+#include "common.cuh"
+
+struct IngestParams {
+    const float* src;      // [n, d] fp32, dense
+    uint8_t* dst;          // row storage, first destination row
+    uint64_t pitch_bytes;  // destination pitch
+    uint64_t n;
+    int d;
+    int d_pad;             // destination elements per row (zero padded)
+};
+
+template <int STORE>
+__device__ __forceinline__ void store_elem(uint8_t* row, int col, float v) {
+    if (STORE == 0)
+        reinterpret_cast<float*>(row)[col] = v;
+    else
+        reinterpret_cast<__nv_bfloat16*>(row)[col] = __float2bfloat16_rn(v);
+}
+
+template <int STORE, int NORMALIZE, int VEC>
+__global__ void __launch_bounds__(256) ingest_rows_kernel(const IngestParams p) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t warps_total = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const int nchunk = (p.d + 3) >> 2;
+    for (uint64_t row = warp_global; row < p.n; row += warps_total) {
+        const float* src = p.src + row * (uint64_t)p.d;
+        uint8_t* dst = p.dst + row * p.pitch_bytes;
+        float scale_den = 1.0f;
+        bool zero = false;
+        if (NORMALIZE) {
+            float acc = 0.0f;
+            for (int c = lane; c < nchunk; c += 32) {
+                if (VEC) {
+                    float4 v = *reinterpret_cast<const float4*>(src + 4 * c);
+                    acc = fmaf(v.x, v.x, acc);
+                    acc = fmaf(v.y, v.y, acc);
+                    acc = fmaf(v.z, v.z, acc);
+                    acc = fmaf(v.w, v.w, acc);
+                } else {
+                    for (int e = 4 * c; e < 4 * c + 4 && e < p.d; ++e) {
+                        float v = src[e];
+                        acc = fmaf(v, v, acc);
+                    }
+                }
+            }
+            acc = warp_sum_xor(acc);
+            float nrm = __fsqrt_rn(acc);
+            zero = ((double)nrm <= 1e-8);  // memo_cli.py:133 compares against the double 1e-8
+            scale_den = nrm;
+        }
+        for (int c = lane; c < (p.d_pad >> 2); c += 32) {
+            float v[4];
+            if (VEC && 4 * c + 3 < p.d) {
+                float4 t = *reinterpret_cast<const float4*>(src + 4 * c);
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = (4 * c + j < p.d) ? src[4 * c + j] : 0.0f;
+            }
+            if (NORMALIZE) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = zero ? 0.0f : __fdiv_rn(v[j], scale_den);
+            }
+            if (STORE == 0) {
+                *reinterpret_cast<float4*>(dst + 16 * (size_t)c) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+                __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+                __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+                uint2 w;
+                w.x = *reinterpret_cast<uint32_t*>(&a);
+                w.y = *reinterpret_cast<uint32_t*>(&b);
+                *reinterpret_cast<uint2*>(dst + 8 * (size_t)c) = w;
+            }
+        }
+    }
+}
+
+// u(seed,row,col) in [-1,1) written as dense fp32 [n,d]
+__global__ void __launch_bounds__(256) synth_rows_kernel(float* out, uint64_t n, uint32_t d,
+                                                         uint64_t seed, uint64_t first_row) {
+    const uint64_t total = n * (uint64_t)d;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        uint64_t row = i / d;
+        uint32_t col = (uint32_t)(i - row * d);
+        out[i] = b200_synth_value(seed, first_row + row, d, col);
+    }
+}
+
+__global__ void __launch_bounds__(256) iota_ids_kernel(int64_t* out, uint64_t n, int64_t first) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = first + (int64_t)i;
+}

@@ -1,0 +1,407 @@
+// scan_topk.cuh — K2: the single / small-batch query GEMV scan with a fused top-k.
+//
+// Replaces index.search(x[nq,d], k) for nq < ~20 (memo_cli.py:292 -> faiss IndexFlat::search,
+// "seq" path [upstream]).  HBM-bound: every database row is read exactly once per launch,
+// nothing but the final [nq,k] result is written.
+//
+//   VARIANT_BULK : every warp owns a private ring of shared-memory stages that it fills itself
+//                  with 1-D cp.async.bulk (TMA engine, SASS UBLKCP) and consumes with 128-bit
+//                  LDS.  No block-level synchronisation in the main loop.
+//   VARIANT_LDG  : same arithmetic, rows read with ld.global.nc.L1::no_allocate.v4 straight
+//                  into registers.  Universal fallback (any row pitch) and the A/B partner for
+//                  the ncu evidence.
+//
+// Both produce bit-identical scores: lane l accumulates 16-byte chunks l, l+32, ... of the row
+// in ascending element order with fmaf, then a 16/8/4/2/1 xor butterfly
+// (oracle/flat_oracle.c: oracle_score_device_order restates exactly this order).
+//
+// Top-k: per warp an unsorted k-entry list of 64-bit keys in shared memory plus the running
+// threshold tau = worst key kept; a row is inserted only when its key beats tau (rare after
+// warm-up: ~k*ln(rows_per_warp/k) inserts per warp per scan).  At the end of the scan the CTA
+// bitonic-sorts its warps' lists, writes its best k keys, and the LAST CTA to finish (atomic
+// ticket) merges all CTA partials, translates row -> record id (K5) and writes D/I — so a search
+// is a single launch.
+#pragma once
+#include "common.cuh"
+
+#define B200_VARIANT_BULK 1
+#define B200_VARIANT_LDG 2
+
+#define B200_SCAN_THREADS_MAX 256
+#define B200_FUSED_K_MAX 256
+#define B200_FINAL_BUF_KEYS 2048
+
+struct ScanParams {
+    const uint8_t* rows;      // row storage
+    uint64_t pitch_bytes;     // bytes per row (multiple of 16)
+    uint32_t nvec;            // 16-byte vectors per row
+    uint64_t n;               // rows
+    const float* q;           // queries of this launch [nqb, d] (device)
+    int d;                    // logical dimension
+    int qstride;              // padded floats per query in shared memory (multiple of 8)
+    int nqb;                  // queries in this launch (<= QB)
+    int k;                    // results per query (top-k mode)
+    uint64_t* partials;       // [grid, QB, k] per-CTA best keys
+    unsigned int* ticket;     // zero before launch; reset by the last CTA
+    float* D;                 // [nqb, k] out
+    int64_t* I;               // [nqb, k] out
+    const int64_t* id_map;    // row -> record id, or null
+    int64_t id_base;          // added to the row when id_map is null
+    uint32_t tile_rows;       // rows per tile (multiple of RB)
+    uint32_t stages;          // BULK: stages per warp
+    uint32_t tile_bytes;      // BULK: tile_rows * pitch_bytes
+    int evict_first;          // BULK: L2 evict-first hint on the stream
+    uint32_t* score_keys;     // full-rank mode: [nqb, n] hi keys, else null
+    uint32_t scratch_keys;    // power of two >= max(warps*k, B200_FINAL_BUF_KEYS)
+};
+
+// ---- small device pieces ---------------------------------------------------------------------
+template <int METRIC>
+__device__ __forceinline__ void acc1(float& a, float v, float q) {
+    if (METRIC == 0) {
+        a = fmaf(v, q, a);
+    } else {
+        float t = v - q;
+        a = fmaf(t, t, a);
+    }
+}
+template <int METRIC>
+__device__ __forceinline__ void acc_f32x4(float& a, const uint4& raw, const float4& q) {
+    acc1<METRIC>(a, __uint_as_float(raw.x), q.x);
+    acc1<METRIC>(a, __uint_as_float(raw.y), q.y);
+    acc1<METRIC>(a, __uint_as_float(raw.z), q.z);
+    acc1<METRIC>(a, __uint_as_float(raw.w), q.w);
+}
+template <int METRIC>
+__device__ __forceinline__ void acc_bf16x8(float& a, const uint4& raw, const float4& qa,
+                                           const float4& qb) {
+    acc1<METRIC>(a, __uint_as_float(raw.x << 16), qa.x);
+    acc1<METRIC>(a, __uint_as_float(raw.x & 0xffff0000u), qa.y);
+    acc1<METRIC>(a, __uint_as_float(raw.y << 16), qa.z);
+    acc1<METRIC>(a, __uint_as_float(raw.y & 0xffff0000u), qa.w);
+    acc1<METRIC>(a, __uint_as_float(raw.z << 16), qb.x);
+    acc1<METRIC>(a, __uint_as_float(raw.z & 0xffff0000u), qb.y);
+    acc1<METRIC>(a, __uint_as_float(raw.w << 16), qb.z);
+    acc1<METRIC>(a, __uint_as_float(raw.w & 0xffff0000u), qb.w);
+}
+
+// Replace the current worst entry of a warp's list with `key`, then recompute the worst.
+__device__ __forceinline__ void warp_list_insert(uint64_t* list, int k, int lane, uint64_t key,
+                                                 uint64_t& tau, int& tau_pos) {
+    if (lane == 0) list[tau_pos] = key;
+    __syncwarp();
+    uint64_t m = ~0ull;
+    int mp = 0;
+    for (int i = lane; i < k; i += 32) {
+        uint64_t v = list[i];
+        if (v < m) {
+            m = v;
+            mp = i;
+        }
+    }
+    uint64_t wm = warp_min_u64(m);
+    unsigned b = __ballot_sync(B200_FULL_MASK, m == wm);
+    int src = __ffs(b) - 1;
+    tau = wm;
+    tau_pos = __shfl_sync(B200_FULL_MASK, mp, src);
+}
+
+// In-place descending bitonic sort of m (power of two) keys in shared memory by the whole CTA.
+__device__ __forceinline__ void cta_bitonic_sort_desc(uint64_t* a, uint32_t m) {
+    for (uint32_t size = 2; size <= m; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+                uint32_t lo = 2 * t - (t & (stride - 1));  // index with bit `stride` clear
+                uint32_t hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint64_t x = a[lo], y = a[hi];
+                bool swap = desc ? (x < y) : (x > y);
+                if (swap) {
+                    a[lo] = y;
+                    a[hi] = x;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---- the kernel --------------------------------------------------------------------------------
+template <int METRIC, int STORE, int QB, int RB, int VARIANT>
+__global__ void __launch_bounds__(B200_SCAN_THREADS_MAX)
+scan_topk_kernel(const ScanParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nw = blockDim.x >> 5;
+    const bool fullrank = (p.score_keys != nullptr);
+    const int k = p.k;
+
+    // ---- shared memory carve-up (host computes the same sizes: scan_smem_bytes) ----
+    // [ring: nw*stages*tile_bytes | scratch (aliases ring start)] [queries] [lists] [mbarriers] [ctr]
+    uint32_t ring_bytes = (VARIANT == B200_VARIANT_BULK) ? nw * p.stages * p.tile_bytes : 0u;
+    uint32_t scratch_bytes = p.scratch_keys * 8u;
+    uint32_t region0 = ring_bytes > scratch_bytes ? ring_bytes : scratch_bytes;
+    region0 = (region0 + 127u) & ~127u;
+    uint8_t* ring = smem;
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem);
+    float* qs = reinterpret_cast<float*>(smem + region0);
+    uint32_t q_bytes = (uint32_t)QB * p.qstride * 4u;
+    uint64_t* lists = reinterpret_cast<uint64_t*>(smem + region0 + q_bytes);
+    uint32_t list_bytes = fullrank ? 0u : (uint32_t)nw * QB * k * 8u;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + region0 + q_bytes + list_bytes);
+    unsigned int* sctr = reinterpret_cast<unsigned int*>(bars + nw * (VARIANT == B200_VARIANT_BULK ? p.stages : 0u));
+    __shared__ unsigned int s_is_last;
+
+    // ---- stage queries (zero padded) and clear lists ----
+    for (int i = threadIdx.x; i < QB * p.qstride; i += blockDim.x) {
+        int qi = i / p.qstride, c = i - qi * p.qstride;
+        qs[i] = (qi < p.nqb && c < p.d) ? p.q[(size_t)qi * p.d + c] : 0.0f;
+    }
+    if (!fullrank)
+        for (int i = threadIdx.x; i < nw * QB * k; i += blockDim.x) lists[i] = 0ull;
+
+    const uint32_t TR = p.tile_rows;
+    const uint64_t tiles_total = (p.n + TR - 1) / TR;
+    const uint64_t gw = (uint64_t)blockIdx.x * nw + warp;
+    const uint64_t GW = (uint64_t)gridDim.x * nw;
+
+    uint32_t bar0 = 0, ring0 = 0;
+    uint64_t policy = 0;
+    if (VARIANT == B200_VARIANT_BULK) {
+        bar0 = smem_u32(bars + warp * p.stages);
+        ring0 = smem_u32(ring + (size_t)warp * p.stages * p.tile_bytes);
+        if (lane == 0) {
+            for (uint32_t s = 0; s < p.stages; ++s) mbar_init(bar0 + 8u * s, 1u);
+            mbar_fence_init();
+        }
+        if (p.evict_first) policy = l2_policy_evict_first();
+    }
+    __syncthreads();
+
+    auto issue = [&](uint32_t s, uint64_t t) {
+        uint64_t row0 = t * TR;
+        uint64_t nr = p.n - row0 < TR ? p.n - row0 : TR;
+        uint32_t bytes = (uint32_t)(nr * p.pitch_bytes);
+        uint32_t bar = bar0 + 8u * s;
+        mbar_arrive_expect_tx(bar, bytes);
+        if (p.evict_first)
+            bulk_g2s_hint(ring0 + s * p.tile_bytes, p.rows + row0 * p.pitch_bytes, bytes, bar, policy);
+        else
+            bulk_g2s(ring0 + s * p.tile_bytes, p.rows + row0 * p.pitch_bytes, bytes, bar);
+    };
+
+    if (VARIANT == B200_VARIANT_BULK) {
+        if (lane == 0) {
+            for (uint32_t s = 0; s < p.stages; ++s) {
+                uint64_t t = gw + (uint64_t)s * GW;
+                if (t < tiles_total) issue(s, t);
+            }
+        }
+    }
+
+    uint64_t tau[QB];
+    int tau_pos[QB];
+#pragma unroll
+    for (int qi = 0; qi < QB; ++qi) {
+        tau[qi] = 0ull;
+        tau_pos[qi] = 0;
+    }
+    uint64_t* my_lists = lists + (size_t)warp * QB * k;
+    const float4* q4 = reinterpret_cast<const float4*>(qs);
+    const int qstride4 = p.qstride >> 2;
+    const uint32_t nvec = p.nvec;
+
+    uint32_t it = 0;
+    for (uint64_t t = gw; t < tiles_total; t += GW, ++it) {
+        const uint64_t tile_row0 = t * TR;
+        const uint32_t rows_in_tile = (uint32_t)(p.n - tile_row0 < TR ? p.n - tile_row0 : TR);
+        uint32_t s = 0;
+        const uint8_t* tile_smem = nullptr;
+        if (VARIANT == B200_VARIANT_BULK) {
+            s = it % p.stages;
+            uint32_t parity = (it / p.stages) & 1u;
+            mbar_wait(bar0 + 8u * s, parity);
+            tile_smem = ring + ((size_t)warp * p.stages + s) * p.tile_bytes;
+        }
+        for (uint32_t g = 0; g < rows_in_tile; g += RB) {
+            float acc[QB][RB];
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi)
+#pragma unroll
+                for (int r = 0; r < RB; ++r) acc[qi][r] = 0.0f;
+
+            const uint8_t* rp[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                if (VARIANT == B200_VARIANT_BULK) {
+                    rp[r] = tile_smem + (size_t)(g + r) * p.pitch_bytes;  // stale rows are discarded below
+                } else {
+                    uint64_t row = tile_row0 + g + r;
+                    if (row >= p.n) row = p.n - 1;
+                    rp[r] = p.rows + row * p.pitch_bytes;
+                }
+            }
+#pragma unroll 2
+            for (uint32_t c = lane; c < nvec; c += 32) {
+                uint4 raw[RB];
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    if (VARIANT == B200_VARIANT_BULK)
+                        raw[r] = *reinterpret_cast<const uint4*>(rp[r] + (size_t)c * 16);
+                    else
+                        raw[r] = ldg_nc_v4(rp[r] + (size_t)c * 16);
+                }
+                if (STORE == 0) {
+#pragma unroll
+                    for (int qi = 0; qi < QB; ++qi) {
+                        float4 qv = q4[qi * qstride4 + c];
+#pragma unroll
+                        for (int r = 0; r < RB; ++r) acc_f32x4<METRIC>(acc[qi][r], raw[r], qv);
+                    }
+                } else {
+#pragma unroll
+                    for (int qi = 0; qi < QB; ++qi) {
+                        float4 qa = q4[qi * qstride4 + 2 * c];
+                        float4 qb = q4[qi * qstride4 + 2 * c + 1];
+#pragma unroll
+                        for (int r = 0; r < RB; ++r) acc_bf16x8<METRIC>(acc[qi][r], raw[r], qa, qb);
+                    }
+                }
+            }
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi)
+#pragma unroll
+                for (int r = 0; r < RB; ++r) acc[qi][r] = warp_sum_xor(acc[qi][r]);
+
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) {
+                if (qi >= p.nqb) break;
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    if (g + r >= rows_in_tile) break;
+                    const uint64_t row = tile_row0 + g + r;
+                    const float sc = acc[qi][r];
+                    const bool valid = b200_score_valid<METRIC>(sc);
+                    if (fullrank) {
+                        if (lane == 0)
+                            p.score_keys[(size_t)qi * p.n + row] = valid ? b200_key_hi<METRIC>(sc) : 0u;
+                    } else if (valid) {
+                        uint64_t key = b200_make_key<METRIC>(sc, (uint32_t)row);
+                        if (key > tau[qi])
+                            warp_list_insert(my_lists + (size_t)qi * k, k, lane, key, tau[qi], tau_pos[qi]);
+                    }
+                }
+            }
+        }
+        if (VARIANT == B200_VARIANT_BULK) {
+            __syncwarp();
+            uint64_t tn = t + (uint64_t)p.stages * GW;
+            if (lane == 0 && tn < tiles_total) issue(s, tn);
+        }
+    }
+
+    if (fullrank) return;
+
+    // ---- CTA merge: the warps' lists -> this CTA's best k per query ----
+    __syncthreads();  // all warps done; every issued bulk copy has been consumed
+    uint32_t m = 2;
+    while (m < (uint32_t)(nw * k)) m <<= 1;
+    for (int qi = 0; qi < p.nqb; ++qi) {
+        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+            uint64_t v = 0ull;
+            if (i < (uint32_t)(nw * k)) {
+                uint32_t w = i / k, j = i - w * k;
+                v = lists[((size_t)w * QB + qi) * k + j];
+            }
+            scratch[i] = v;
+        }
+        cta_bitonic_sort_desc(scratch, m);
+        uint64_t* out = p.partials + ((size_t)blockIdx.x * QB + qi) * k;
+        for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = scratch[i];
+        __syncthreads();
+    }
+
+    // ---- last CTA: merge all partials, translate ids, write D/I ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned prev = atomicAdd(p.ticket, 1u);
+        s_is_last = (prev == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    for (int qi = 0; qi < p.nqb; ++qi) {
+        // scratch[0..k) holds the running best (sorted); whole CTA lists are appended behind it,
+        // filtered against the running k-th best, and the buffer is re-sorted when it fills up.
+        for (uint32_t i = threadIdx.x; i < p.scratch_keys; i += blockDim.x) scratch[i] = 0ull;
+        if (threadIdx.x == 0) *sctr = (unsigned)k;
+        __syncthreads();
+        const uint32_t B = p.scratch_keys;
+        uint32_t cta = 0;
+        while (cta < gridDim.x) {
+            // how many whole CTA lists fit in the free part of the buffer
+            uint32_t filled = *sctr;
+            uint32_t fit = (B - filled) / (uint32_t)k;
+            if (fit == 0) fit = 1;  // cannot happen: B >= 2k is guaranteed by the host
+            uint32_t take = gridDim.x - cta < fit ? gridDim.x - cta : fit;
+            uint64_t tau_now = scratch[k - 1];
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < take * (uint32_t)k; i += blockDim.x) {
+                uint32_t c = cta + i / k, j = i % k;
+                uint64_t key = __ldcg(p.partials + ((size_t)c * QB + qi) * k + j);
+                if (key > tau_now) {
+                    unsigned slot = atomicAdd(sctr, 1u);
+                    scratch[slot] = key;
+                }
+            }
+            cta += take;
+            __syncthreads();
+            filled = *sctr;
+            bool last_round = (cta >= gridDim.x);
+            bool full = (B - filled) < (uint32_t)k;
+            if (last_round || full) {
+                uint32_t mm = 2;
+                while (mm < filled) mm <<= 1;
+                for (uint32_t i = filled + threadIdx.x; i < mm; i += blockDim.x) scratch[i] = 0ull;
+                cta_bitonic_sort_desc(scratch, mm);
+                for (uint32_t i = (uint32_t)k + threadIdx.x; i < mm; i += blockDim.x) scratch[i] = 0ull;
+                __syncthreads();
+                if (threadIdx.x == 0) *sctr = (unsigned)k;
+                __syncthreads();
+            }
+        }
+        for (int i = threadIdx.x; i < k; i += blockDim.x) {
+            uint64_t key = scratch[i];
+            float dist;
+            int64_t id;
+            if (key == 0ull) {
+                dist = (METRIC == 0) ? -FLT_MAX : FLT_MAX;
+                id = -1;
+            } else {
+                dist = b200_key_score(key, METRIC);
+                uint32_t row = b200_key_row(key);
+                id = p.id_map ? p.id_map[row] : (int64_t)row + p.id_base;
+            }
+            p.D[(size_t)qi * k + i] = dist;
+            p.I[(size_t)qi * k + i] = id;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *p.ticket = 0u;  // ready for the next launch on this stream
+}
+
+// shared memory the kernel needs for a configuration (host side twin of the carve-up above)
+static inline size_t scan_smem_bytes(int variant, int nw, int QB, int qstride, int k, bool fullrank,
+                                     uint32_t stages, uint32_t tile_bytes, uint32_t scratch_keys) {
+    size_t ring = variant == B200_VARIANT_BULK ? (size_t)nw * stages * tile_bytes : 0;
+    size_t scratch = (size_t)scratch_keys * 8;
+    size_t region0 = ring > scratch ? ring : scratch;
+    region0 = (region0 + 127) & ~(size_t)127;
+    size_t q = (size_t)QB * qstride * 4;
+    size_t lists = fullrank ? 0 : (size_t)nw * QB * k * 8;
+    size_t bars = variant == B200_VARIANT_BULK ? (size_t)nw * stages * 8 : 0;
+    return region0 + q + lists + bars + 16;
+}

@@ -1,0 +1,391 @@
+"""The faiss-shaped Python surface memo drives (memo_cli.py:13 `import faiss`), over the C ABI.
+
+Exactly the symbols memo_cli.py touches plus the flat classes north_star names:
+
+    IndexFlat / IndexFlatIP / IndexFlatL2      restated target of create_index(), memo_cli.py:244-248
+    IndexHNSWFlat(d, M)                        constructor memo calls (:245); mapped to an exact flat
+                                               L2 index (k = ntotal makes HNSW exhaustive anyway, :291)
+    IndexIDMap / IndexIDMap2                   :248, isinstance checks :258
+    .add_with_ids(x, ids) .add(x) .search(x,k) :282 :437 :292
+    .ntotal .id_map  vector_to_array()         :266 :268 :289 :291 :473
+    read_index / write_index                   :255 :361 :448
+    normalize_L2                               faiss helper, the K1 kernel as a function
+
+All arithmetic runs in the sm_100a kernels behind include/b200_flat.h.  There is no CPU path:
+without the native library or a CUDA device every call raises RuntimeError.
+Error convention follows faiss: RuntimeError for engine failures, AssertionError for shape checks.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import _cabi
+
+METRIC_INNER_PRODUCT = 0
+METRIC_L2 = 1
+
+_FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def _default_device() -> int:
+    for var in ("B200_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(var)
+        if v is not None and v.strip().lstrip("-").isdigit():
+            return int(v)
+    return 0
+
+
+class Int64Vector:
+    """Stand-in for faiss's std::vector<int64> wrapper (`index.id_map`, memo_cli.py:268)."""
+
+    def __init__(self, arr: np.ndarray):
+        self._arr = np.ascontiguousarray(arr, dtype=np.int64)
+
+    def size(self) -> int:
+        return int(self._arr.shape[0])
+
+    def at(self, i: int) -> int:
+        return int(self._arr[i])
+
+    def __len__(self) -> int:
+        return self.size()
+
+
+def vector_to_array(v) -> np.ndarray:
+    """faiss.vector_to_array (memo_cli.py:268): a fresh numpy copy of the vector."""
+    if isinstance(v, Int64Vector):
+        return v._arr.copy()
+    return np.array(v, copy=True)
+
+
+class Index:
+    """Common base (faiss.Index)."""
+
+    d: int
+    metric_type: int
+    is_trained = True
+    verbose = False
+
+    @property
+    def ntotal(self) -> int:
+        raise NotImplementedError
+
+    def train(self, x) -> None:  # flat indexes need no training [upstream]
+        return None
+
+
+class IndexFlat(Index):
+    """Exhaustive index resident in HBM.  `store` = "f32" | "bf16"; `normalize` L2-normalises rows
+    at add time and queries at search time (cosine as IP over unit vectors, memo_cli.py:131-135)."""
+
+    def __init__(self, d: int, metric: int = METRIC_L2, *, store: str = "f32", normalize: bool = False,
+                 device: int | None = None):
+        self._h = C.c_void_p()
+        self.d = int(d)
+        self.metric_type = int(metric)
+        self.store = store
+        self.normalize = bool(normalize)
+        self.device = _default_device() if device is None else int(device)
+        st = {"f32": _cabi.STORE_F32, "fp32": _cabi.STORE_F32, "bf16": _cabi.STORE_BF16}.get(store)
+        if st is None:
+            raise ValueError(f"unknown store {store!r}")
+        L = _cabi.load()
+        _cabi.check(L.b200_index_create(C.byref(self._h), self.d, self.metric_type, st, self.device))
+        if self.normalize:
+            self.set_option("normalize_queries", 1)
+
+    # -- lifetime --
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), C.c_void_p()
+        if h is not None and h.value:
+            _cabi.load().b200_index_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- options (sweep harness / bench) --
+    def set_option(self, name: str, value: int) -> None:
+        _cabi.check(_cabi.load().b200_index_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        out = C.c_int64(0)
+        _cabi.check(_cabi.load().b200_index_get_option(self._h, name.encode(), C.byref(out)))
+        return out.value
+
+    # -- faiss surface --
+    @property
+    def ntotal(self) -> int:
+        return int(_cabi.load().b200_index_ntotal(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(_cabi.load().b200_index_launch_count(self._h))
+
+    def reserve(self, n_total: int) -> None:
+        _cabi.check(_cabi.load().b200_index_reserve(self._h, int(n_total)))
+
+    def reset(self) -> None:
+        _cabi.check(_cabi.load().b200_index_reset(self._h))
+
+    def _coerce_x(self, x) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.ndim == 2, "expected a 2-D array [n, d]"
+        assert x.shape[1] == self.d, f"vector dimension {x.shape[1]} != index dimension {self.d}"
+        return x
+
+    def add(self, x) -> None:
+        x = self._coerce_x(x)
+        _cabi.check(_cabi.load().b200_index_add(self._h, x.ctypes.data, x.shape[0], None, int(self.normalize)))
+
+    def add_with_ids(self, x, ids) -> None:
+        raise RuntimeError("add_with_ids not implemented for this type of index")  # as faiss [upstream]
+
+    def _add_with_ids(self, x, ids) -> None:
+        x = self._coerce_x(x)
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        assert ids.shape == (x.shape[0],), "not same number of vectors and ids"
+        _cabi.check(_cabi.load().b200_index_add(self._h, x.ctypes.data, x.shape[0], ids.ctypes.data, int(self.normalize)))
+
+    def add_synthetic(self, n: int, seed: int, first_row: int = 0, *, with_ids: bool = False, first_id: int = 0) -> None:
+        """Rows u(seed,row,col) generated on the device; for databases too large to upload."""
+        _cabi.check(_cabi.load().b200_index_add_synthetic(self._h, int(n), int(seed), int(first_row),
+                                                          int(self.normalize), int(with_ids), int(first_id)))
+
+    def search(self, x, k: int):
+        x = self._coerce_x(x)
+        k = int(k)
+        assert k > 0
+        nq = x.shape[0]
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        _cabi.check(_cabi.load().b200_index_search(self._h, x.ctypes.data, nq, k, D.ctypes.data, I.ctypes.data))
+        return D, I
+
+    def search_device(self, q, k: int, D=None, I=None, stream: int | None = None):
+        """Device-resident search: q/D/I are torch CUDA tensors on this index's device; the work is
+        enqueued on `stream` (a raw cudaStream_t, default torch's current stream), not synchronised."""
+        import torch
+
+        assert q.is_cuda and q.dtype == torch.float32 and q.is_contiguous() and q.dim() == 2 and q.shape[1] == self.d
+        nq = q.shape[0]
+        if D is None:
+            D = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+        if I is None:
+            I = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(q.device).cuda_stream
+        if not stream:
+            stream = 1  # cudaStreamLegacy: torch's default stream (NULL would mean the handle's own stream)
+        _cabi.check(_cabi.load().b200_index_search_dev(self._h, q.data_ptr(), nq, int(k), D.data_ptr(), I.data_ptr(),
+                                                       C.c_void_p(stream)))
+        return D, I
+
+    def sync(self) -> None:
+        _cabi.check(_cabi.load().b200_index_sync(self._h))
+
+    def reconstruct_n(self, i0: int = 0, n: int | None = None) -> np.ndarray:
+        n = self.ntotal - i0 if n is None else int(n)
+        out = np.empty((n, self.d), dtype=np.float32)
+        if n:
+            _cabi.check(_cabi.load().b200_index_get_rows(self._h, int(i0), n, out.ctypes.data))
+        return out
+
+    def reconstruct(self, i: int) -> np.ndarray:
+        return self.reconstruct_n(int(i), 1)[0]
+
+    def _ids(self) -> np.ndarray:
+        out = np.empty((self.ntotal,), dtype=np.int64)
+        if out.size:
+            _cabi.check(_cabi.load().b200_index_get_ids(self._h, out.ctypes.data))
+        return out
+
+
+class IndexFlatIP(IndexFlat):
+    def __init__(self, d: int, **kw):
+        super().__init__(d, METRIC_INNER_PRODUCT, **kw)
+
+
+class IndexFlatL2(IndexFlat):
+    def __init__(self, d: int, **kw):
+        super().__init__(d, METRIC_L2, **kw)
+
+
+class IndexHNSWFlat(IndexFlat):
+    """memo constructs IndexHNSWFlat(384, 32) and sets hnsw.efConstruction / hnsw.efSearch
+    (memo_cli.py:245-247) but always searches with k = ntotal (:291), i.e. exhaustively.  This class
+    accepts the same constructor and attribute writes and is an exact flat index."""
+
+    def __init__(self, d: int, M: int = 32, metric: int = METRIC_L2, **kw):
+        super().__init__(d, metric, **kw)
+        self.hnsw = SimpleNamespace(efConstruction=40, efSearch=16, M=int(M))
+
+
+class IndexIDMap(Index):
+    """faiss.IndexIDMap: user ids over a base index; ids are translated inside the search kernel."""
+
+    _fourcc = b"IxMp"
+
+    def __init__(self, index: IndexFlat):
+        if not isinstance(index, IndexFlat):
+            raise RuntimeError("IndexIDMap: only flat base indexes are supported")
+        if index.ntotal != 0 and not getattr(index, "_idmap_adopt", False):
+            raise RuntimeError("index must be empty on input")  # as faiss [upstream]
+        self.index = index
+        self.own_fields = True
+        self.d = index.d
+        self.metric_type = index.metric_type
+
+    @property
+    def ntotal(self) -> int:
+        return self.index.ntotal
+
+    @property
+    def id_map(self) -> Int64Vector:
+        return Int64Vector(self.index._ids())
+
+    def add_with_ids(self, x, ids) -> None:
+        self.index._add_with_ids(x, ids)
+
+    def add(self, x) -> None:
+        raise RuntimeError("add does not make sense with IndexIDMap, use add_with_ids")  # as faiss
+
+    def search(self, x, k: int):
+        return self.index.search(x, k)
+
+    def search_device(self, q, k: int, **kw):
+        return self.index.search_device(q, k, **kw)
+
+    def reset(self) -> None:
+        self.index.reset()
+
+    def reserve(self, n_total: int) -> None:
+        self.index.reserve(n_total)
+
+
+class IndexIDMap2(IndexIDMap):
+    """IndexIDMap plus reconstruct-by-id (reverse map built on demand)."""
+
+    _fourcc = b"IxM2"
+
+    def reconstruct(self, key: int) -> np.ndarray:
+        ids = self.index._ids()
+        pos = np.nonzero(ids == int(key))[0]
+        if pos.size == 0:
+            raise RuntimeError(f"key {key} not found")
+        return self.index.reconstruct(int(pos[-1]))
+
+
+# ------------------------------------------------------------------------------------------------
+# normalize_L2 — K1 as a function
+# ------------------------------------------------------------------------------------------------
+def normalize_L2(x: np.ndarray, device: int | None = None) -> None:
+    """In-place row normalisation on the device with memo's semantics (memo_cli.py:131-135)."""
+    assert isinstance(x, np.ndarray) and x.dtype == np.float32 and x.ndim == 2 and x.flags.c_contiguous
+    dev = _default_device() if device is None else device
+    _cabi.check(_cabi.load().b200_normalize_rows(x.ctypes.data, x.shape[0], x.shape[1], dev))
+
+
+# ------------------------------------------------------------------------------------------------
+# .memo files — faiss's native index serialisation [upstream layout]
+# ------------------------------------------------------------------------------------------------
+def _write_header(f, idx: Index, ntotal: int) -> None:
+    f.write(struct.pack("<i", idx.d))
+    f.write(struct.pack("<q", ntotal))
+    f.write(struct.pack("<q", 1 << 20))
+    f.write(struct.pack("<q", 1 << 20))
+    f.write(struct.pack("<B", 1))
+    f.write(struct.pack("<i", idx.metric_type))
+
+
+def _read_header(f):
+    d, = struct.unpack("<i", _read_exact(f, 4))
+    ntotal, _d1, _d2 = struct.unpack("<qqq", _read_exact(f, 24))
+    _trained, = struct.unpack("<B", _read_exact(f, 1))
+    metric, = struct.unpack("<i", _read_exact(f, 4))
+    if metric > 1:
+        _read_exact(f, 4)  # metric_arg
+    if d <= 0 or ntotal < 0:
+        raise RuntimeError("corrupt index header")
+    return d, ntotal, metric
+
+
+def _read_exact(f, n: int) -> bytes:
+    b = f.read(n)
+    if len(b) != n:
+        raise RuntimeError(f"read error: wanted {n} bytes, got {len(b)}")
+    return b
+
+
+def _write_flat(f, idx: IndexFlat) -> None:
+    f.write(b"IxFI" if idx.metric_type == METRIC_INNER_PRODUCT else b"IxF2")
+    n = idx.ntotal
+    _write_header(f, idx, n)
+    f.write(struct.pack("<Q", n * idx.d))  # code bytes / 4
+    step = max(1, (64 << 20) // (idx.d * 4))
+    for i0 in range(0, n, step):
+        idx.reconstruct_n(i0, min(step, n - i0)).tofile(f)
+
+
+def write_index(index: Index, path: str) -> None:
+    """faiss.write_index (memo_cli.py:361, :448).  bf16-stored rows are widened to fp32 (lossless)."""
+    with open(path, "wb") as f:
+        if isinstance(index, IndexIDMap):
+            f.write(index._fourcc)
+            _write_header(f, index, index.ntotal)
+            _write_flat(f, index.index)
+            ids = index.index._ids()
+            f.write(struct.pack("<Q", ids.shape[0]))
+            ids.tofile(f)
+        elif isinstance(index, IndexFlat):
+            _write_flat(f, index)
+        else:
+            raise RuntimeError(f"don't know how to serialize {type(index).__name__}")
+
+
+def _read_any(f, device):
+    fourcc = _read_exact(f, 4)
+    if fourcc in (b"IxMp", b"IxM2"):
+        d, ntotal, metric = _read_header(f)
+        # the nested flat payload must be added together with the ids that follow it
+        base, rows = _read_flat_payload(f, device)
+        n_ids, = struct.unpack("<Q", _read_exact(f, 8))
+        if n_ids != rows.shape[0]:
+            raise RuntimeError("id_map size does not match the nested index")
+        ids = np.frombuffer(_read_exact(f, 8 * n_ids), dtype="<i8").astype(np.int64)
+        wrapper = (IndexIDMap2 if fourcc == b"IxM2" else IndexIDMap)(base)
+        if n_ids:
+            wrapper.add_with_ids(rows, ids)
+        return wrapper
+    f.seek(-4, os.SEEK_CUR)
+    base, rows = _read_flat_payload(f, device)
+    if rows.shape[0]:
+        base.add(rows)
+    return base
+
+
+def _read_flat_payload(f, device):
+    fourcc = _read_exact(f, 4)
+    if fourcc not in (b"IxFI", b"IxF2", b"IxFl"):
+        raise RuntimeError(f"Index type {fourcc!r} not recognized")
+    d, ntotal, metric = _read_header(f)
+    count, = struct.unpack("<Q", _read_exact(f, 8))
+    if count != ntotal * d:
+        raise RuntimeError("flat payload size does not match header")
+    rows = np.frombuffer(_read_exact(f, 4 * count), dtype="<f4").astype(np.float32).reshape(ntotal, d)
+    base = IndexFlat(d, metric, device=device)
+    return base, rows
+
+
+def read_index(path: str, device: int | None = None) -> Index:
+    """faiss.read_index (memo_cli.py:255): raises on a missing or corrupt file (memo catches
+    Exception and starts a fresh index, :256-257)."""
+    with open(path, "rb") as f:
+        return _read_any(f, device)

@@ -1,0 +1,138 @@
+/*
+ * b200_flat.h — C ABI of the B200-native flat vector recall path.
+ *
+ * This is the drop-in boundary for the one hot path of memo (mikesmullin/c99-vectordb v2):
+ * the flat (exhaustive) IP / L2 / cosine search and the index rebuild (add) that
+ * /root/reference/memo_cli.py drives through the `faiss` module object it imports at
+ * memo_cli.py:13.  Every entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain C types only: pointers, sizes, ints.  No C++ exceptions cross this boundary.
+ *   - every function returns an int status: 0 = ok, non-zero = failure; the message for the
+ *     calling thread is then available from b200_last_error().
+ *   - "host" pointers are ordinary process memory (numpy buffers); "dev" pointers are CUDA
+ *     device pointers on the index's device (torch tensors' data_ptr()).
+ *   - one CUDA stream per handle; calls on one handle are serialised by the caller
+ *     (memo is single-threaded, memo_cli.py:883-949).  Different handles are independent:
+ *     there is no global mutable state.
+ *   - there is NO CPU fallback: with no usable CUDA device every compute entry fails loudly.
+ *
+ * Tie rule (stated): results are ordered by (score best-first, then smaller
+ * row position first); at the k-th boundary the smaller row position is kept.
+ */
+#ifndef B200_FLAT_H
+#define B200_FLAT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+/* metric: faiss MetricType values [upstream faiss/MetricType.h]: IP = 0, L2 = 1 */
+#define B200_METRIC_IP 0
+#define B200_METRIC_L2 1
+
+/* row storage */
+#define B200_STORE_F32 0
+#define B200_STORE_BF16 1
+
+/* search path selection (b200_index_set_option "scan_variant") */
+#define B200_SCAN_AUTO 0
+#define B200_SCAN_BULK 1 /* cp.async.bulk (TMA) staged smem ring */
+#define B200_SCAN_LDG 2  /* direct 128-bit ld.global.nc */
+
+typedef struct b200_index b200_index;
+
+/* ---- library ---------------------------------------------------------------------------- */
+
+int b200_abi_version(void);
+/* message of the last failure on the calling thread ("" if none) */
+const char* b200_last_error(void);
+/* number of CUDA devices visible; fails (non-zero) when the CUDA runtime is unusable */
+int b200_device_count(int* out_count);
+
+/* ---- index lifetime ---------------------------------------------------------------------
+ * replaces: faiss.IndexHNSWFlat(DIM, 32) / faiss.IndexIDMap2(base) construction,
+ *           memo_cli.py:244-248 (restated as IndexFlatIP / IndexFlatL2 per north_star). */
+int b200_index_create(b200_index** out, int d, int metric, int store, int device);
+int b200_index_destroy(b200_index* ix);
+/* drop all rows, keep the allocation (faiss Index::reset [upstream]) */
+int b200_index_reset(b200_index* ix);
+/* make room for n_total rows without reallocation */
+int b200_index_reserve(b200_index* ix, int64_t n_total);
+/* named integer options: "scan_variant", "scan_warps", "scan_stages", "scan_tile_rows",
+ * "scan_ctas_per_sm", "scan_l2_evict_first", "fullrank_min_k" — tuning knobs for the sweep
+ * harness; defaults are the measured best. */
+int b200_index_set_option(b200_index* ix, const char* name, int64_t value);
+int b200_index_get_option(b200_index* ix, const char* name, int64_t* out_value);
+
+/* ---- add (index rebuild) ------------------------------------------------------------------
+ * replaces: index.add_with_ids(x[n,d] float32, ids[n] int64), memo_cli.py:282 and :437,
+ *           and (normalize=1) memo's normalize(), memo_cli.py:131-135, run at add time.
+ * x is row-major contiguous [n,d]; ids may be NULL (then id == row position, faiss Index::add).
+ * Both arrays are copied; the caller keeps ownership.  Mixing NULL and non-NULL ids on one
+ * index is an error once rows exist. */
+int b200_index_add(b200_index* ix, const float* x_host, int64_t n, const int64_t* ids_host,
+                   int normalize);
+int b200_index_add_dev(b200_index* ix, const float* x_dev, int64_t n, const int64_t* ids_dev,
+                       int normalize);
+/* synthetic rows generated on the device by the counter-based generator of DESIGN.md §6
+ * (bit-identical to oracle/flat_oracle.c:oracle_synth_rows); rows get ids first_id + i when
+ * with_ids != 0.  Used by bench.py / tests for databases too large to upload. */
+int b200_index_add_synthetic(b200_index* ix, int64_t n, uint64_t seed, int64_t first_row,
+                             int normalize, int with_ids, int64_t first_id);
+
+/* ---- search -------------------------------------------------------------------------------
+ * replaces: D, I = index.search(x[nq,d] float32, k), memo_cli.py:292
+ *           (IndexIDMap2::search over IndexFlatIP/IndexFlatL2 [upstream]).
+ * D is float32 [nq,k], I is int64 [nq,k], best-first, padded with id -1 and
+ * -FLT_MAX (IP) / +FLT_MAX (L2).  Any k >= 1 is accepted (memo asks for k = ntotal,
+ * memo_cli.py:291). */
+int b200_index_search(b200_index* ix, const float* q_host, int64_t nq, int64_t k, float* D_host,
+                      int64_t* I_host);
+/* device-resident variant: q, D, I are device pointers; work is enqueued on `stream`
+ * (a cudaStream_t; NULL = the handle's own stream) and NOT synchronised. */
+int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev,
+                          int64_t* I_dev, void* stream);
+/* kernel launches issued by this handle since creation (bench.py's gpu_launches) */
+int64_t b200_index_launch_count(b200_index* ix);
+/* block until the handle's stream is idle */
+int b200_index_sync(b200_index* ix);
+
+/* ---- introspection ------------------------------------------------------------------------
+ * replaces: index.ntotal (memo_cli.py:266,:289,:291,:473);
+ *           faiss.vector_to_array(index.id_map) (memo_cli.py:268);
+ *           the row payload faiss.write_index serialises (memo_cli.py:361,:448). */
+int64_t b200_index_ntotal(b200_index* ix);
+int b200_index_d(b200_index* ix);
+int b200_index_metric(b200_index* ix);
+int b200_index_store(b200_index* ix);
+int b200_index_has_ids(b200_index* ix);
+int b200_index_get_ids(b200_index* ix, int64_t* out_host /* [ntotal] */);
+/* rows [row0, row0+n) as float32 [n,d] (bf16 storage is widened exactly) */
+int b200_index_get_rows(b200_index* ix, int64_t row0, int64_t n, float* out_host);
+/* device pointer to the row storage and its pitch in bytes (for zero-copy callers) */
+int b200_index_rows_dev(b200_index* ix, void** out_ptr, size_t* out_pitch_bytes);
+
+/* ---- stand-alone stages ---------------------------------------------------------------------
+ * K1 as a function: in-place L2 normalisation of host rows on the device
+ * (faiss.normalize_L2 surface; memo normalize(), memo_cli.py:131-135: norm <= 1e-8 -> zeros). */
+int b200_normalize_rows(float* x_host, int64_t n, int d, int device);
+/* K4/K5: merge G per-shard result lists (shard-major [G,nq,k], each list best-first) into
+ * [nq,k]; ties go to the lower shard, then to the earlier position in that shard's list, which
+ * is the global smaller-row-first rule for contiguous row-range shards.  Device pointers. */
+int b200_merge_topk_dev(int metric, int G, int64_t nq, int64_t k, const float* D_parts_dev,
+                        const int64_t* I_parts_dev, float* D_out_dev, int64_t* I_out_dev,
+                        void* stream);
+/* counter-based synthetic rows written to a device buffer [n,d] float32 */
+int b200_synth_rows_dev(float* out_dev, int64_t n, int d, uint64_t seed, int64_t first_row,
+                        int normalize, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_FLAT_H */

@@ -1,0 +1,204 @@
+"""ctypes face of oracle/flat_oracle.c plus a small numpy twin.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; nothing under c99_vectordb_b200/ does.  PARITY UNPINNED for the search
+arithmetic (no faiss in this image, no golden vectors in the reference) — see flat_oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+SRC = HERE / "flat_oracle.c"
+LIB = HERE / "_build" / "liboracle.so"
+
+METRIC_IP, METRIC_L2 = 0, 1
+ORDER_SIMD, ORDER_DEVICE = 0, 1
+
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    if not force and LIB.exists() and LIB.stat().st_mtime >= SRC.stat().st_mtime:
+        return LIB
+    LIB.parent.mkdir(parents=True, exist_ok=True)
+    subprocess.run(
+        ["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-shared", "-std=c11",
+         "-ffp-contract=off", "-o", str(LIB), str(SRC), "-lm"],
+        check=True,
+    )
+    return LIB
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(LIB))
+        fp, ip, dp = C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_double)
+        L.oracle_synth_rows.argtypes = [fp, C.c_int64, C.c_int, C.c_uint64, C.c_int64]
+        L.oracle_synth_rows.restype = None
+        L.oracle_round_bf16.argtypes = [fp, C.c_int64]
+        L.oracle_round_bf16.restype = None
+        L.oracle_scores.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int64, C.c_int, fp, fp]
+        L.oracle_scores.restype = None
+        L.oracle_scores_f64.argtypes = [C.c_int, fp, C.c_int64, C.c_int, fp, dp]
+        L.oracle_scores_f64.restype = None
+        for name in ("oracle_search", "oracle_search_rowpar"):
+            f = getattr(L, name)
+            f.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int64, C.c_int, ip, fp, C.c_int64, C.c_int64, fp, ip]
+            f.restype = C.c_int
+        L.oracle_normalize_rows.argtypes = [fp, C.c_int64, C.c_int, C.c_int]
+        L.oracle_normalize_rows.restype = None
+        L.oracle_merge_topk.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, fp, ip, fp, ip]
+        L.oracle_merge_topk.restype = None
+        L.oracle_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _pf(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _pi(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def max_threads() -> int:
+    return int(lib().oracle_max_threads())
+
+
+def synth_rows(n: int, d: int, seed: int, first_row: int = 0) -> np.ndarray:
+    out = np.empty((n, d), dtype=np.float32)
+    lib().oracle_synth_rows(_pf(out), n, d, seed, first_row)
+    return out
+
+
+def round_bf16(x: np.ndarray) -> np.ndarray:
+    y = _f32(x).copy()
+    lib().oracle_round_bf16(_pf(y), y.size)
+    return y
+
+
+def normalize_rows(x: np.ndarray, order: int = ORDER_SIMD) -> np.ndarray:
+    """memo_cli.py:131-135 applied to every row."""
+    y = np.atleast_2d(_f32(x)).copy()
+    lib().oracle_normalize_rows(_pf(y), y.shape[0], y.shape[1], order)
+    return y.reshape(np.shape(x))
+
+
+def scores(metric: int, db: np.ndarray, q: np.ndarray, order: int = ORDER_SIMD, chunk: int = 4) -> np.ndarray:
+    db, q = _f32(db), _f32(q).reshape(-1)
+    out = np.empty(db.shape[0], dtype=np.float32)
+    lib().oracle_scores(metric, order, chunk, _pf(db), db.shape[0], db.shape[1], _pf(q), _pf(out))
+    return out
+
+
+def scores_f64(metric: int, db: np.ndarray, q: np.ndarray) -> np.ndarray:
+    db, q = _f32(db), _f32(q).reshape(-1)
+    out = np.empty(db.shape[0], dtype=np.float64)
+    lib().oracle_scores_f64(metric, _pf(db), db.shape[0], db.shape[1], _pf(q), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out
+
+
+def search(metric: int, db: np.ndarray, q: np.ndarray, k: int, ids: np.ndarray | None = None,
+           order: int = ORDER_SIMD, chunk: int = 4, rowpar: bool = False):
+    """index.search(q, k) over a flat index holding `db` (memo_cli.py:292)."""
+    db = _f32(db)
+    q = np.atleast_2d(_f32(q))
+    n, d = db.shape if db.ndim == 2 else (0, q.shape[1])
+    nq = q.shape[0]
+    D = np.empty((nq, k), dtype=np.float32)
+    I = np.empty((nq, k), dtype=np.int64)
+    idp = None
+    if ids is not None:
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        idp = _pi(ids)
+    fn = lib().oracle_search_rowpar if rowpar else lib().oracle_search
+    rc = fn(metric, order, chunk, _pf(db), n, d, idp, _pf(q), nq, k, _pf(D), _pi(I))
+    if rc:
+        raise MemoryError("oracle_search")
+    return D, I
+
+
+def merge_topk(metric: int, D_parts: np.ndarray, I_parts: np.ndarray):
+    """[G,nq,k] shard-major best-first lists -> [nq,k] (K4 restatement)."""
+    Dp, Ip = _f32(D_parts), np.ascontiguousarray(I_parts, dtype=np.int64)
+    G, nq, k = Dp.shape
+    Do = np.empty((nq, k), dtype=np.float32)
+    Io = np.empty((nq, k), dtype=np.int64)
+    lib().oracle_merge_topk(metric, G, nq, k, _pf(Dp), _pi(Ip), _pf(Do), _pi(Io))
+    return Do, Io
+
+
+# ---- numpy twin (cross-checks the C oracle; fp64 ranking) ----------------------------------------
+
+def np_search_f64(metric: int, db: np.ndarray, q: np.ndarray, k: int, ids: np.ndarray | None = None):
+    """Brute-force ranking in float64 with the stated tie rule (stable sort => smaller row first)."""
+    db64 = np.asarray(db, dtype=np.float64)
+    q64 = np.atleast_2d(np.asarray(q, dtype=np.float64))
+    nq, n = q64.shape[0], db64.shape[0]
+    D = np.full((nq, k), -np.finfo(np.float32).max if metric == METRIC_IP else np.finfo(np.float32).max, dtype=np.float64)
+    I = np.full((nq, k), -1, dtype=np.int64)
+    for i in range(nq):
+        if metric == METRIC_IP:
+            s = db64 @ q64[i]
+            order = np.argsort(-s, kind="stable")
+        else:
+            s = ((db64 - q64[i]) ** 2).sum(axis=1)
+            order = np.argsort(s, kind="stable")
+        m = min(k, n)
+        rows = order[:m]
+        D[i, :m] = s[rows]
+        I[i, :m] = rows if ids is None else np.asarray(ids)[rows]
+    return D, I
+
+
+def check_topk_against_truth(metric: int, db: np.ndarray, q: np.ndarray, D: np.ndarray, I: np.ndarray,
+                             rows_of_ids=None, rel_eps: float = 1e-5):
+    """Adjudicated parity check of one result list against the fp64 truth (SURVEY.md §7 hard part 1).
+
+    Passes iff (a) every returned distance is within rel_eps of the fp64 score of its row, and
+    (b) the returned rows are a valid top-k: every row NOT returned has an fp64 score that is not
+    better than the worst returned one by more than rel_eps (relative), and the returned order is
+    best-first up to rel_eps.  Returns a list of human-readable violations (empty == pass).
+    """
+    q = np.asarray(q, dtype=np.float32).reshape(-1)
+    truth = scores_f64(metric, db, q)
+    sign = -1.0 if metric == METRIC_IP else 1.0  # smaller sign*score is better
+    bad: list[str] = []
+    rows = np.asarray(I if rows_of_ids is None else [rows_of_ids[int(i)] if i >= 0 else -1 for i in I], dtype=np.int64)
+    valid = rows >= 0
+    got = rows[valid]
+    if len(set(got.tolist())) != len(got):
+        bad.append("duplicate rows in result")
+    if len(got) != min(len(rows), db.shape[0]):
+        bad.append(f"expected {min(len(rows), db.shape[0])} valid results, got {len(got)}")
+    scale = max(1.0, float(np.max(np.abs(truth))) if truth.size else 1.0)
+    tol = rel_eps * scale
+    for pos, (r, dist) in enumerate(zip(rows, np.asarray(D, dtype=np.float64))):
+        if r < 0:
+            continue
+        if abs(dist - truth[r]) > rel_eps * max(1.0, abs(truth[r])):
+            bad.append(f"pos {pos}: distance {dist} vs fp64 {truth[r]}")
+    t = sign * truth[got]
+    if np.any(np.diff(t) < -tol):
+        bad.append("result not best-first within tolerance")
+    if len(got):
+        worst = np.max(t)
+        mask = np.ones(db.shape[0], dtype=bool)
+        mask[got] = False
+        if mask.any():
+            best_out = np.min(sign * truth[mask])
+            if best_out < worst - tol:
+                bad.append(f"a better row was left out: outside {best_out} vs worst kept {worst}")
+    return bad
