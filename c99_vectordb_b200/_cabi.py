@@ -46,7 +46,7 @@ SIGNATURES = [
     ("b200_index_get_rows", C.c_int, [_h, C.c_int64, C.c_int64, C.c_void_p]),
     ("b200_index_rows_dev", C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     ("b200_normalize_rows", C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int]),
-    ("b200_merge_topk_dev", C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("b200_merge_topk_dev", C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("b200_synth_rows_dev", C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
 ]
 

@@ -620,7 +620,6 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
             CK(cudaStreamSynchronize(st));
             CKI(grow(&ix->qn_dev, &ix->qn_cap, (size_t)nq * ix->d));
         }
-        if (ix->d % 4 != 0) return fail("normalize_queries needs d %% 4 == 0");
         CKI(ingest_dev(ix->d, ix->d, B200_STORE_F32, q_dev, (uint8_t*)ix->qn_dev, (size_t)ix->d * 4, nq, 1,
                        ix->num_sms, st, &ix->launches));
         q_dev = ix->qn_dev;
@@ -813,17 +812,19 @@ extern "C" int b200_normalize_rows(float* x_host, int64_t n, int d, int device) 
 }
 
 extern "C" int b200_merge_topk_dev(int metric, int G, int64_t nq, int64_t k, const float* D_parts_dev,
-                                   const int64_t* I_parts_dev, float* D_out_dev, int64_t* I_out_dev, void* stream) {
+                                   const int64_t* I_parts_dev, int64_t D_part_stride, int64_t I_part_stride,
+                                   float* D_out_dev, int64_t* I_out_dev, void* stream) {
     if (G <= 0 || nq < 0 || k <= 0) return fail("bad shape");
     if (nq == 0) return 0;
     if (!D_parts_dev || !I_parts_dev || !D_out_dev || !I_out_dev) return fail("null buffer");
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ds = D_part_stride ? D_part_stride : nq * k, is = I_part_stride ? I_part_stride : nq * k;
     int64_t total = (int64_t)G * nq * k;
     unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16);
     if (metric == B200_METRIC_IP)
-        merge_topk_kernel<0><<<blocks, 256, 0, st>>>(G, nq, k, D_parts_dev, I_parts_dev, D_out_dev, I_out_dev);
+        merge_topk_kernel<0><<<blocks, 256, 0, st>>>(G, nq, k, D_parts_dev, I_parts_dev, ds, is, D_out_dev, I_out_dev);
     else if (metric == B200_METRIC_L2)
-        merge_topk_kernel<1><<<blocks, 256, 0, st>>>(G, nq, k, D_parts_dev, I_parts_dev, D_out_dev, I_out_dev);
+        merge_topk_kernel<1><<<blocks, 256, 0, st>>>(G, nq, k, D_parts_dev, I_parts_dev, ds, is, D_out_dev, I_out_dev);
     else
         return fail("unknown metric %d", metric);
     CK(cudaGetLastError());

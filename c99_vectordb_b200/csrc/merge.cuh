@@ -31,7 +31,8 @@ __device__ __forceinline__ int64_t count_better(const float* D, const int64_t* I
 template <int METRIC>
 __global__ void __launch_bounds__(256)
 merge_topk_kernel(int G, int64_t nq, int64_t k, const float* __restrict__ Dp,
-                  const int64_t* __restrict__ Ip, float* __restrict__ Do, int64_t* __restrict__ Io) {
+                  const int64_t* __restrict__ Ip, int64_t dstride, int64_t istride,
+                  float* __restrict__ Do, int64_t* __restrict__ Io) {
     const int64_t total = (int64_t)G * nq * k;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
@@ -40,16 +41,16 @@ merge_topk_kernel(int G, int64_t nq, int64_t k, const float* __restrict__ Dp,
         int64_t r = t - q * (G * k);
         int g = (int)(r / k);
         int64_t j = r - (int64_t)g * k;
-        const float* Dme = Dp + ((int64_t)g * nq + q) * k;
-        const int64_t* Ime = Ip + ((int64_t)g * nq + q) * k;
+        const float* Dme = Dp + (int64_t)g * dstride + q * k;
+        const int64_t* Ime = Ip + (int64_t)g * istride + q * k;
         float s = Dme[j];
         int64_t id = Ime[j];
         uint32_t h = merge_hi<METRIC>(s, id);
         int64_t rank = j;
         for (int g2 = 0; g2 < G; ++g2) {
             if (g2 == g) continue;
-            const float* D2 = Dp + ((int64_t)g2 * nq + q) * k;
-            const int64_t* I2 = Ip + ((int64_t)g2 * nq + q) * k;
+            const float* D2 = Dp + (int64_t)g2 * dstride + q * k;
+            const int64_t* I2 = Ip + (int64_t)g2 * istride + q * k;
             rank += count_better<METRIC>(D2, I2, k, h, /*or_equal=*/g2 < g);
         }
         if (rank < k) {

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) ingest_rows_kernel(const IngestParams p) 
             zero = ((double)nrm <= 1e-8);  // memo_cli.py:133 compares against the double 1e-8
             scale_den = nrm;
         }
-        for (int c = lane; c < (p.d_pad >> 2); c += 32) {
+        for (int c = lane; c < ((p.d_pad + 3) >> 2); c += 32) {
             float v[4];
             if (VEC && 4 * c + 3 < p.d) {
                 float4 t = *reinterpret_cast<const float4*>(src + 4 * c);
@@ -71,7 +71,13 @@ __global__ void __launch_bounds__(256) ingest_rows_kernel(const IngestParams p) 
                 for (int j = 0; j < 4; ++j) v[j] = zero ? 0.0f : __fdiv_rn(v[j], scale_den);
             }
             if (STORE == 0) {
-                *reinterpret_cast<float4*>(dst + 16 * (size_t)c) = make_float4(v[0], v[1], v[2], v[3]);
+                if ((p.pitch_bytes & 15) == 0) {
+                    *reinterpret_cast<float4*>(dst + 16 * (size_t)c) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {  // dense destination with d % 4 != 0 (normalised query scratch)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (4 * c + j < p.d) reinterpret_cast<float*>(dst)[4 * c + j] = v[j];
+                }
             } else {
                 __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
                 __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);

@@ -1,0 +1,176 @@
+"""Row-sharded flat index across the GPUs of one box: one process per GPU (torch.distributed).
+
+The reference has no distributed code (single process, memo_cli.py:883-949); this is the multi-GPU
+restatement north_star specifies for index.search (memo_cli.py:292): rows are split into contiguous
+ranges, rank g owning [g*ceil(N/G), (g+1)*ceil(N/G)); every rank runs the scan kernel over its
+shard (ids are translated to GLOBAL record ids inside the kernel), the per-rank best-first lists
+are exchanged with ONE all-gather of a packed (I,D) buffer (NCCL over NVLink/NVSwitch), and the K4
+kernel merges them on every rank.  Contiguous ranges make "lower rank first, then earlier list
+position" equal to the global tie rule (smaller row position first).
+
+torch is plumbing only: device buffers, the stream, and the process group.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from . import index as _ix
+
+
+def shard_range(n_total: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous row range [lo, hi) of `rank`; the last ranks may be short or empty."""
+    per = -(-int(n_total) // int(world)) if n_total > 0 else 0
+    lo = min(n_total, rank * per)
+    hi = min(n_total, (rank + 1) * per)
+    return lo, hi
+
+
+def _packed_layout(nq: int, k: int) -> tuple[int, int, int]:
+    """Per-rank exchange buffer: int64 I[nq,k] first (8-byte aligned), then float32 D[nq,k];
+    padded to 16 bytes.  Returns (bytes, offset_of_D, bytes_of_I)."""
+    ib = nq * k * 8
+    db = nq * k * 4
+    total = (ib + db + 15) // 16 * 16
+    return total, ib, ib
+
+
+class ShardedIndexFlat:
+    """faiss-shaped add/search over a row-sharded database.
+
+    `local_index` / `merge_fn` / `device` exist so the host logic (partitioning, exchange layout,
+    rank-major merge order) can be exercised on CPU with the gloo backend in tests; the defaults
+    are the CUDA index and the K4 kernel and nothing else ships.
+    """
+
+    def __init__(self, d: int, metric: int = _ix.METRIC_L2, *, store: str = "f32", normalize: bool = False,
+                 group=None, local_index=None, merge_fn=None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        self.d, self.metric_type = int(d), int(metric)
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if local_index is None:
+            dev_index = torch.cuda.current_device()
+            self.device = torch.device("cuda", dev_index)
+            local_index = _ix.IndexIDMap2(_ix.IndexFlat(d, metric, store=store, normalize=normalize, device=dev_index))
+        else:
+            self.device = torch.device(device or "cpu")
+        self.local = local_index
+        self._merge_fn = merge_fn
+        self.ntotal_global = 0
+        self.merge_launches = 0
+        self._bufs = {}
+
+    # ---- add --------------------------------------------------------------------------------
+    def add_with_ids(self, x: np.ndarray, ids: np.ndarray) -> None:
+        """Every rank is handed the same [n,d] block; it keeps the rows of its contiguous range."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        assert x.ndim == 2 and x.shape[1] == self.d and ids.shape == (x.shape[0],)
+        if self.ntotal_global != 0:
+            raise RuntimeError("ShardedIndexFlat takes its rows in one add (contiguous ranges per rank)")
+        lo, hi = shard_range(x.shape[0], self.world, self.rank)
+        if hi > lo:
+            self.local.add_with_ids(x[lo:hi], ids[lo:hi])
+        self.ntotal_global = x.shape[0]
+
+    def add(self, x: np.ndarray) -> None:
+        self.add_with_ids(x, np.arange(np.shape(x)[0], dtype=np.int64))
+
+    def add_synthetic(self, n_total: int, seed: int) -> None:
+        """Each rank generates its own range of the counter-based database on its device; ids are the
+        global row positions."""
+        if self.ntotal_global != 0:
+            raise RuntimeError("ShardedIndexFlat takes its rows in one add")
+        lo, hi = shard_range(n_total, self.world, self.rank)
+        if hi > lo:
+            self.local.index.add_synthetic(hi - lo, seed, first_row=lo, with_ids=True, first_id=lo)
+        self.ntotal_global = int(n_total)
+
+    @property
+    def ntotal(self) -> int:
+        return self.ntotal_global
+
+    @property
+    def launch_count(self) -> int:
+        base = getattr(self.local, "index", self.local)
+        return int(getattr(base, "launch_count", 0)) + self.merge_launches
+
+    # ---- search -----------------------------------------------------------------------------
+    def _buffers(self, nq: int, k: int):
+        import torch
+
+        key = (nq, k)
+        if key not in self._bufs:
+            nbytes, off_d, _ = _packed_layout(nq, k)
+            mine = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            gathered = torch.zeros(self.world * nbytes, dtype=torch.uint8, device=self.device)
+            D = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+            I = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+            self._bufs[key] = (mine, gathered, D, I, nbytes, off_d)
+        return self._bufs[key]
+
+    def search_device(self, q, k: int):
+        """q: [nq,d] float32 tensor on this rank's device (same on every rank).  Returns (D, I)
+        tensors holding the merged global result on every rank.  Enqueued on the current stream."""
+        import torch
+        import torch.distributed as dist
+
+        nq, k = int(q.shape[0]), int(k)
+        mine, gathered, D, I, nbytes, off_d = self._buffers(nq, k)
+        I_loc = mine[: nq * k * 8].view(torch.int64).view(nq, k)
+        D_loc = mine[off_d: off_d + nq * k * 4].view(torch.float32).view(nq, k)
+        self._local_search(q, k, D_loc, I_loc)
+        if self.world == 1:
+            return D_loc, I_loc
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        self._merge(gathered, nq, k, nbytes, off_d, D, I)
+        return D, I
+
+    def search(self, x: np.ndarray, k: int):
+        """Host query -> host result (every rank passes the same query and gets the same answer)."""
+        import torch
+
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        assert x.ndim == 2 and x.shape[1] == self.d
+        if self.device.type == "cuda":
+            host = torch.from_numpy(x).pin_memory()
+            q = host.to(self.device, non_blocking=True)
+        else:
+            q = torch.from_numpy(x)
+        D, I = self.search_device(q, k)
+        return D.cpu().numpy(), I.cpu().numpy()
+
+    # ---- pieces -----------------------------------------------------------------------------
+    def _local_search(self, q, k, D_loc, I_loc) -> None:
+        if self.device.type == "cuda":
+            self.local.search_device(q, k, D=D_loc, I=I_loc)
+        else:  # injected test index: numpy in, numpy out
+            import torch
+
+            Dn, In = self.local.search(q.numpy(), k)
+            D_loc.copy_(torch.from_numpy(np.ascontiguousarray(Dn)))
+            I_loc.copy_(torch.from_numpy(np.ascontiguousarray(In)))
+
+    def _merge(self, gathered, nq, k, nbytes, off_d, D, I) -> None:
+        import torch
+
+        if self._merge_fn is not None:
+            g = gathered.view(self.world, nbytes)
+            Ip = g[:, : nq * k * 8].contiguous().view(torch.int64).view(self.world, nq, k)
+            Dp = g[:, off_d: off_d + nq * k * 4].contiguous().view(torch.float32).view(self.world, nq, k)
+            Dm, Im = self._merge_fn(self.metric_type, Dp.numpy(), Ip.numpy())
+            D.copy_(torch.from_numpy(Dm))
+            I.copy_(torch.from_numpy(Im))
+            return
+        stream = torch.cuda.current_stream(self.device).cuda_stream or 1
+        base = gathered.data_ptr()
+        _cabi.check(_cabi.load().b200_merge_topk_dev(
+            self.metric_type, self.world, nq, k, C.c_void_p(base + off_d), C.c_void_p(base), nbytes // 4, nbytes // 8,
+            D.data_ptr(), I.data_ptr(), C.c_void_p(stream)))
+        self.merge_launches += 1

@@ -124,10 +124,12 @@ int b200_index_rows_dev(b200_index* ix, void** out_ptr, size_t* out_pitch_bytes)
 int b200_normalize_rows(float* x_host, int64_t n, int d, int device);
 /* K4/K5: merge G per-shard result lists (shard-major [G,nq,k], each list best-first) into
  * [nq,k]; ties go to the lower shard, then to the earlier position in that shard's list, which
- * is the global smaller-row-first rule for contiguous row-range shards.  Device pointers. */
+ * is the global smaller-row-first rule for contiguous row-range shards.  Device pointers.
+ * Shard g's lists start at D_parts + g*D_part_stride / I_parts + g*I_part_stride (in elements;
+ * 0 means the dense nq*k), so one packed all-gather buffer can be merged in place. */
 int b200_merge_topk_dev(int metric, int G, int64_t nq, int64_t k, const float* D_parts_dev,
-                        const int64_t* I_parts_dev, float* D_out_dev, int64_t* I_out_dev,
-                        void* stream);
+                        const int64_t* I_parts_dev, int64_t D_part_stride, int64_t I_part_stride,
+                        float* D_out_dev, int64_t* I_out_dev, void* stream);
 /* counter-based synthetic rows written to a device buffer [n,d] float32 */
 int b200_synth_rows_dev(float* out_dev, int64_t n, int d, uint64_t seed, int64_t first_row,
                         int normalize, void* stream);

@@ -1,0 +1,368 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (c99_vectordb_b200/_cabi.py ->
+_b200flat.so), against the CPU oracle on the same seeded inputs.
+
+Bars: ids bit-exact; distances bit-exact against the oracle's device-order summation and within
+1e-5 relative of the fp64 truth (the tolerance north_star states for fp32).  Near-ties in fp32
+are adjudicated by oracle.check_topk_against_truth.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+FLT_MAX = np.finfo(np.float32).max
+VARIANTS = {"bulk": 1, "ldg": 2}
+
+
+@pytest.fixture(scope="module")
+def b200(gpu):
+    import c99_vectordb_b200 as m
+
+    return m
+
+
+def assert_same_ranking_mod_near_ties(ids_got, ids_ref, scores_ref, eps):
+    """Positions i, i+1 belong to one group when the reference scores differ by <= eps; within a
+    group the id SETS must match, across groups the order must match."""
+    assert len(ids_got) == len(ids_ref)
+    start = 0
+    n = len(ids_ref)
+    for i in range(1, n + 1):
+        if i == n or abs(float(scores_ref[i]) - float(scores_ref[i - 1])) > eps:
+            assert sorted(ids_got[start:i]) == sorted(ids_ref[start:i]), (start, i, ids_got[start:i], ids_ref[start:i])
+            start = i
+
+
+def make_index(m, metric, d, db, ids=None, store="f32", variant=None, normalize=False):
+    base = m.IndexFlat(d, metric, store=store, normalize=normalize)
+    if variant:
+        base.set_option("scan_variant", VARIANTS[variant])
+    if ids is None:
+        if len(db):
+            base.add(db)
+        return base
+    w = m.IndexIDMap2(base)
+    if len(db):
+        w.add_with_ids(db, ids)
+    return w
+
+
+SHAPES = [
+    # n, d, k, nq
+    (1, 1, 1, 1),
+    (5, 3, 4, 2),
+    (33, 7, 10, 3),
+    (1000, 64, 10, 1),
+    (4099, 100, 17, 5),
+    (10000, 384, 10, 8),
+    (10000, 384, 10, 13),
+    (20011, 768, 10, 1),
+    (20011, 768, 100, 2),
+    (7001, 1024, 256, 1),
+    (3000, 2048, 10, 4),
+    (257, 4100, 5, 1),     # row pitch too large for the staged ring at 8 warps
+    (64, 20000, 3, 2),     # falls back to the direct-load variant
+]
+
+
+@pytest.mark.parametrize("variant", ["bulk", "ldg"])
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("n,d,k,nq", SHAPES)
+def test_fused_topk_bit_exact_vs_device_order_oracle(b200, variant, metric, n, d, k, nq):
+    db = oracle.synth_rows(n, d, 1234)
+    q = oracle.synth_rows(nq, d, 5678)
+    idx = make_index(b200, metric, d, db, variant=variant)
+    D, I = idx.search(q, k)
+    Dw, Iw = oracle.search(metric, db, q, k, order=oracle.ORDER_DEVICE, chunk=4)
+    np.testing.assert_array_equal(I, Iw)
+    np.testing.assert_array_equal(D, Dw)
+    for i in range(nq):
+        assert oracle.check_topk_against_truth(metric, db, q[i], D[i], I[i]) == []
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_matches_faiss_order_oracle_ids(b200, metric):
+    """Against the SIMD-order restatement (the faiss-like summation): ids exact on well separated
+    data, distances within 1e-5 relative."""
+    n, d, k, nq = 50000, 384, 10, 16
+    db = oracle.normalize_rows(oracle.synth_rows(n, d, 1234))
+    q = oracle.normalize_rows(oracle.synth_rows(nq, d, 5678))
+    idx = make_index(b200, metric, d, db)
+    D, I = idx.search(q, k)
+    Dw, Iw = oracle.search(metric, db, q, k)
+    np.testing.assert_array_equal(I, Iw)
+    np.testing.assert_allclose(D, Dw, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("variant", ["bulk", "ldg"])
+@pytest.mark.parametrize("metric", [0, 1])
+def test_exact_ties_and_boundary(b200, variant, metric):
+    base = oracle.synth_rows(500, 48, 3)
+    db = np.concatenate([base, base, base[:100], base])  # every row has 3-4 exact duplicates
+    q = oracle.synth_rows(4, 48, 4)
+    idx = make_index(b200, metric, 48, db, variant=variant)
+    for k in (1, 2, 3, 7, 64, 256):
+        D, I = idx.search(q, k)
+        Dw, Iw = oracle.search(metric, db, q, k, order=oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_padding_empty_and_k_larger_than_ntotal(b200, metric):
+    pad = -FLT_MAX if metric == 0 else FLT_MAX
+    q = oracle.synth_rows(3, 16, 2)
+    empty = make_index(b200, metric, 16, np.zeros((0, 16), np.float32))
+    D, I = empty.search(q, 5)
+    assert (I == -1).all() and (D == pad).all() and empty.ntotal == 0
+    db = oracle.synth_rows(3, 16, 1)
+    idx = make_index(b200, metric, 16, db)
+    for k in (6, 40, 300):  # fused path and full-rank path
+        D, I = idx.search(q, k)
+        Dw, Iw = oracle.search(metric, db, q, k, order=oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)
+        assert (I[:, 3:] == -1).all() and (D[:, 3:] == pad).all()
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_nan_inf_rows_never_returned(b200, metric):
+    db = oracle.synth_rows(300, 32, 1)
+    db[2, 3] = np.nan
+    db[50, 0] = np.inf if metric == 1 else -np.inf
+    db[299, 31] = np.nan
+    q = np.abs(oracle.synth_rows(2, 32, 2)) + 0.1
+    idx = make_index(b200, metric, 32, db)
+    for k in (10, 300, 400):
+        D, I = idx.search(q, k)
+        Dw, Iw = oracle.search(metric, db, q, k, order=oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)
+        assert not np.isin(I, [2, 50, 299]).any()
+
+
+def test_idmap2_sparse_ids_and_incremental_adds(b200):
+    """memo adds one row at a time with its record id (memo_cli.py:437); ids are sparse after
+    blank skipping (:278-280)."""
+    d = 384
+    db = oracle.normalize_rows(oracle.synth_rows(200, d, 9))
+    ids = np.cumsum(np.random.default_rng(0).integers(1, 5, 200)).astype(np.int64)
+    idx = make_index(b200, 1, d, db[:150], ids[:150])
+    for i in range(150, 200):
+        idx.add_with_ids(db[i:i + 1], ids[i:i + 1])
+    assert idx.ntotal == 200
+    np.testing.assert_array_equal(b200.vector_to_array(idx.id_map), ids)
+    q = oracle.normalize_rows(oracle.synth_rows(5, d, 10))
+    for k in (10, 200):
+        D, I = idx.search(q, k)
+        Dw, Iw = oracle.search(1, db, q, k, ids=ids, order=oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)
+    with pytest.raises(RuntimeError):
+        idx.add(db[:1])
+    with pytest.raises(AssertionError):
+        idx.search(np.zeros((1, d + 1), np.float32), 3)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("n,d,nq", [(1000, 64, 1), (5000, 384, 3), (70000, 32, 2), (4096 * 3 + 5, 8, 9)])
+def test_full_ranking_k_equals_ntotal(b200, metric, n, d, nq):
+    """search_all asks for k = ntotal (memo_cli.py:291): the radix-sorted full ranking."""
+    db = oracle.synth_rows(n, d, 77)
+    db[n // 2] = db[n // 3]  # an exact tie
+    q = oracle.synth_rows(nq, d, 78)
+    idx = make_index(b200, metric, d, db)
+    D, I = idx.search(q, n)
+    Dw, Iw = oracle.search(metric, db, q, n, order=oracle.ORDER_DEVICE)
+    np.testing.assert_array_equal(I, Iw)
+    np.testing.assert_array_equal(D, Dw)
+    D2, I2 = idx.search(q, 257)  # just above the fused limit
+    np.testing.assert_array_equal(I2, Iw[:, :257])
+
+
+def test_fullrank_and_fused_agree(b200):
+    db, q = oracle.synth_rows(30000, 128, 5), oracle.synth_rows(2, 128, 6)
+    idx = make_index(b200, 0, 128, db)
+    a = idx.search(q, 100)
+    idx.set_option("fullrank_min_k", 1)
+    b = idx.search(q, 100)
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[0], b[0])
+
+
+def test_normalize_matches_reference_golden(b200):
+    g = np.load(GOLDEN / "normalize.npz")
+    for i in range(int(g["n"])):
+        vin, ref = g[f"in_{i}"], g[f"out_{i}"]
+        x = vin.reshape(1, -1).copy()
+        b200.normalize_L2(x)
+        np.testing.assert_allclose(x[0], ref, rtol=3e-7, atol=1e-12, err_msg=f"case {i}")
+        if not ref.any():
+            assert not x.any()
+        np.testing.assert_array_equal(x[0], oracle.normalize_rows(vin, oracle.ORDER_DEVICE))
+
+
+@pytest.mark.parametrize("store", ["f32", "bf16"])
+@pytest.mark.parametrize("d", [5, 384, 1024])
+def test_normalize_at_add_time(b200, store, d):
+    raw = oracle.synth_rows(777, d, 31) * 3.0
+    raw[5] = 0.0
+    idx = b200.IndexFlat(d, 0, store=store, normalize=True)
+    idx.add(raw)
+    want = oracle.normalize_rows(raw, oracle.ORDER_DEVICE)
+    if store == "bf16":
+        want = oracle.round_bf16(want)
+    np.testing.assert_array_equal(idx.reconstruct_n(0, 777), want)
+    q = oracle.synth_rows(3, d, 32)
+    D, I = idx.search(q, 10)  # queries are normalised on the device too
+    qn = oracle.normalize_rows(q, oracle.ORDER_DEVICE)
+    Dw, Iw = oracle.search(0, want, qn, 10, order=oracle.ORDER_DEVICE, chunk=8 if store == "bf16" else 4)
+    np.testing.assert_array_equal(I, Iw)
+    np.testing.assert_array_equal(D, Dw)
+
+
+def test_synthetic_rows_bit_identical_to_oracle(b200):
+    for d, store in ((384, "f32"), (100, "f32"), (1024, "bf16")):
+        idx = b200.IndexFlat(d, 1, store=store)
+        idx.add_synthetic(5000, seed=1234, first_row=0)
+        idx.add_synthetic(3000, seed=1234, first_row=5000)
+        want = oracle.synth_rows(8000, d, 1234)
+        if store == "bf16":
+            want = oracle.round_bf16(want)
+        np.testing.assert_array_equal(idx.reconstruct_n(0, 8000), want)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("variant", ["bulk", "ldg"])
+def test_bf16_storage_bit_exact_and_recall(b200, metric, variant):
+    n, d, k, nq = 30000, 1024, 10, 8
+    db = oracle.normalize_rows(oracle.synth_rows(n, d, 1234))
+    q = oracle.normalize_rows(oracle.synth_rows(nq, d, 5678))
+    idx = make_index(b200, metric, d, db, store="bf16", variant=variant)
+    D, I = idx.search(q, k)
+    db16 = oracle.round_bf16(db)
+    Dw, Iw = oracle.search(metric, db16, q, k, order=oracle.ORDER_DEVICE, chunk=8)
+    np.testing.assert_array_equal(I, Iw)
+    np.testing.assert_array_equal(D, Dw)
+    # bf16 storage is lossy: report recall@k against the fp32 oracle instead of id equality
+    _, I32 = oracle.search(metric, db, q, k)
+    recall = np.mean([len(set(I[i]) & set(I32[i])) / k for i in range(nq)])
+    assert recall >= 0.8, recall
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("G,k,nq", [(2, 10, 1), (8, 10, 5), (3, 100, 4), (8, 1000, 2)])
+def test_merge_kernel_vs_oracle(b200, metric, G, k, nq):
+    import ctypes as C
+    import torch
+
+    from c99_vectordb_b200 import _cabi
+
+    n, d = 900, 16
+    base = oracle.synth_rows(n // 2, d, 9)
+    db = np.concatenate([base, base])
+    q = oracle.synth_rows(nq, d, 8)
+    per = -(-n // G)
+    Dp, Ip = [], []
+    for g in range(G):
+        lo, hi = g * per, min(n, (g + 1) * per)
+        Dg, Ig = oracle.search(metric, db[lo:hi], q, k, ids=np.arange(lo, hi, dtype=np.int64))
+        Dp.append(Dg), Ip.append(Ig)
+    Dp_t = torch.from_numpy(np.stack(Dp)).cuda()
+    Ip_t = torch.from_numpy(np.stack(Ip)).cuda()
+    Do = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    Io = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream or 1
+    _cabi.check(_cabi.load().b200_merge_topk_dev(metric, G, nq, k, Dp_t.data_ptr(), Ip_t.data_ptr(), 0, 0, Do.data_ptr(),
+                                                 Io.data_ptr(), C.c_void_p(st)))
+    torch.cuda.synchronize()
+    Dw, Iw = oracle.merge_topk(metric, np.stack(Dp), np.stack(Ip))
+    np.testing.assert_array_equal(Io.cpu().numpy(), Iw)
+    np.testing.assert_array_equal(Do.cpu().numpy(), Dw)
+    want = oracle.search(metric, db, q, k)
+    np.testing.assert_array_equal(Io.cpu().numpy(), want[1])
+
+
+def test_search_device_tensors(b200):
+    import torch
+
+    db, q = oracle.synth_rows(20000, 384, 1), oracle.synth_rows(4, 384, 2)
+    idx = make_index(b200, 0, 384, db)
+    qt = torch.from_numpy(q).cuda()
+    D, I = idx.search_device(qt, 10)
+    torch.cuda.synchronize()
+    Dw, Iw = oracle.search(0, db, q, 10, order=oracle.ORDER_DEVICE)
+    np.testing.assert_array_equal(I.cpu().numpy(), Iw)
+    np.testing.assert_array_equal(D.cpu().numpy(), Dw)
+
+
+def test_write_read_index_roundtrip(b200, tmp_path):
+    d = 384
+    db = oracle.normalize_rows(oracle.synth_rows(1000, d, 3))
+    ids = np.arange(1000, dtype=np.int64) * 3 + 1
+    idx = make_index(b200, 1, d, db, ids)
+    p = tmp_path / "db.memo"
+    b200.write_index(idx, str(p))
+    raw = p.read_bytes()
+    assert raw[:4] == b"IxM2" and raw[37:41] == b"IxF2"  # faiss layout: wrapper, 33-byte header, nested flat
+    back = b200.read_index(str(p))
+    assert isinstance(back, b200.IndexIDMap2) and back.ntotal == 1000 and back.d == d
+    np.testing.assert_array_equal(b200.vector_to_array(back.id_map), ids)
+    q = oracle.normalize_rows(oracle.synth_rows(2, d, 4))
+    a, b = idx.search(q, 1000), back.search(q, 1000)
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[0], b[0])
+    flat = make_index(b200, 0, d, db)
+    b200.write_index(flat, str(p))
+    back = b200.read_index(str(p))
+    assert isinstance(back, b200.IndexFlat) and back.metric_type == 0 and back.ntotal == 1000
+
+
+def test_memo_adapter_against_reference_golden(b200):
+    """rebuild_index_from_texts / get_existing_ids / search_all mirror memo_cli.py:265-298: compare
+    with what the REFERENCE functions returned (tests/golden/make_golden.py)."""
+    from c99_vectordb_b200 import memo_adapter as ma
+
+    g = np.load(GOLDEN / "adapter.npz", allow_pickle=True)
+    records = [None if r == "\x00NONE" else r for r in g["records"].tolist()]
+    idx = ma.rebuild_index_from_texts(records, vectors=g["kept_vectors"])
+    assert sorted(ma.get_existing_ids(idx)) == g["existing_ids"].tolist()
+    for qv, ids_ref, sc_ref in zip(g["qvecs"], g["res_ids"], g["res_scores"]):
+        res = ma.search_all(idx, qv)
+        np.testing.assert_allclose([r.score for r in res], sc_ref, rtol=1e-5, atol=1e-6)
+        # hashed bag-of-words rows produce many mathematically tied scores whose fp32 values differ
+        # in the last ulp between summation orders: ids must agree exactly outside such groups and
+        # as sets inside them (SURVEY.md §7 hard part 1)
+        assert_same_ranking_mod_near_ties([r.doc_id for r in res], ids_ref.tolist(), sc_ref, eps=2e-6)
+        top = ma.search_all(idx, qv, k=5)
+        assert [r.doc_id for r in top] == [r.doc_id for r in res[:5]]
+    # the embedder mirror: same tokens, same buckets (hash injected so the test is seed independent)
+    e = np.load(GOLDEN / "embed.npz", allow_pickle=True)
+    import zlib
+    h = lambda tok: zlib.crc32(tok.encode())  # noqa: E731
+    v = ma.embed_text_hash("Hello hello WORLD_1  world_1", hash_fn=h)
+    assert abs(float(np.linalg.norm(v)) - 1.0) < 1e-6 and np.count_nonzero(v) <= 2
+    assert e["vectors"].shape[1] == ma.DIM
+
+
+@pytest.mark.parametrize("metric,n,d,norm", [(0, 1_000_000, 768, True), (1, 2_000_000, 384, False)])
+def test_large_scan_against_fp64_truth(b200, metric, n, d, norm):
+    """BASELINE config-1 size (1M x 768 cosine): device-generated rows, fp64 truth on the host."""
+    idx = b200.IndexFlat(d, metric, normalize=norm)
+    idx.add_synthetic(n, seed=1234)
+    db = oracle.synth_rows(n, d, 1234)
+    if norm:
+        db = oracle.normalize_rows(db, oracle.ORDER_DEVICE)
+    q = oracle.synth_rows(4, d, 5678)
+    qn = oracle.normalize_rows(q, oracle.ORDER_DEVICE) if norm else q
+    for variant in ("bulk", "ldg"):
+        idx.set_option("scan_variant", VARIANTS[variant])
+        D, I = idx.search(q, 10)
+        for i in range(4):
+            assert oracle.check_topk_against_truth(metric, db, qn[i], D[i], I[i]) == []
+        Dw, Iw = oracle.search(metric, db, qn, 10, order=oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)

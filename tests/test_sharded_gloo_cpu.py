@@ -1,0 +1,88 @@
+"""world_size-2/3 gloo tests of the multi-GPU host logic (row partitioning, the packed all-gather
+layout, rank-major merge order) on CPU.  The local index and the merge are the ORACLE here
+(injected, test-only); on GPUs the same class runs the CUDA index and the K4 kernel."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import oracle  # noqa: E402
+from c99_vectordb_b200.sharded import ShardedIndexFlat, shard_range, _packed_layout  # noqa: E402
+
+
+class OracleLocalIndex:
+    """add_with_ids / search on the CPU oracle (what one rank's CUDA index does)."""
+
+    def __init__(self, d, metric):
+        self.d, self.metric = d, metric
+        self.rows = np.zeros((0, d), np.float32)
+        self.ids = np.zeros((0,), np.int64)
+
+    def add_with_ids(self, x, ids):
+        self.rows = np.concatenate([self.rows, x])
+        self.ids = np.concatenate([self.ids, ids])
+
+    def search(self, q, k):
+        return oracle.search(self.metric, self.rows, q, k, ids=self.ids)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, metric, n, d, k, nq, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        base = oracle.synth_rows(n // 2, d, 9)
+        db = np.concatenate([base, base, oracle.synth_rows(n - 2 * (n // 2), d, 10)])  # cross-shard exact ties
+        ids = np.arange(n, dtype=np.int64) * 7 + 3
+        q = oracle.synth_rows(nq, d, 8)
+        idx = ShardedIndexFlat(d, metric, local_index=OracleLocalIndex(d, metric), merge_fn=oracle.merge_topk, device="cpu")
+        idx.add_with_ids(db, ids)
+        lo, hi = shard_range(n, world, rank)
+        assert idx.local.rows.shape[0] == hi - lo and idx.ntotal == n
+        D, I = idx.search(q, k)
+        Dw, Iw = oracle.search(metric, db, q, k, ids=ids)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)
+        np.save(os.path.join(out_dir, f"I_{rank}.npy"), I)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,metric,n,k,nq", [(2, 0, 1001, 10, 3), (2, 1, 1001, 10, 1), (3, 1, 50, 40, 2), (2, 0, 3, 5, 2)])
+def test_sharded_search_equals_unsharded(tmp_path, world, metric, n, k, nq):
+    mp.spawn(_worker, args=(world, _free_port(), metric, n, 24, k, nq, str(tmp_path)), nprocs=world, join=True)
+    outs = [np.load(tmp_path / f"I_{r}.npy") for r in range(world)]
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o, outs[0])  # every rank holds the merged answer
+
+
+def test_shard_range_covers_rows_once():
+    for n in (0, 1, 7, 8, 9, 100_000_000):
+        for w in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(hi >= lo for lo, hi in spans)
+
+
+def test_packed_layout_alignment():
+    for nq, k in ((1, 10), (3, 7), (10000, 100), (1, 1)):
+        total, off_d, ib = _packed_layout(nq, k)
+        assert off_d == nq * k * 8 and off_d % 8 == 0 and total % 16 == 0 and total >= nq * k * 12
