@@ -47,6 +47,16 @@ DEFAULT_WORKLOAD = "10Mx768_ip_f32_k10_nq1"
 DB_SEED, Q_SEED = 1234, 5678
 
 
+def scan_passes(nq: int) -> int:
+    """Scan launches one search issues (mirror of pick_qb in csrc/cabi.cu: query blocks of 8/4/2/1)."""
+    passes, rem = 0, nq
+    while rem > 0:
+        qb = 8 if rem >= 8 else 4 if rem > 2 else rem
+        rem -= min(qb, rem)
+        passes += 1
+    return passes
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -290,7 +300,7 @@ def main_b200(a):
     if rank == 0:
         peak, peak_src = measured_peaks()
         launch_bytes = (hi - lo) * d * elem  # algorithmic bytes one scan launch streams on this rank
-        scans_per_step = max(1, round((launches / a.steps) - (1 if world > 1 else 0)))  # nq > 8 -> several passes
+        scans_per_step = scan_passes(nq)  # nq > 8 -> several passes over the database per step
         scan_avg_ms = scan_avg_ms / scans_per_step
         achieved = launch_bytes / (scan_avg_ms * 1e-3) / 1e9
         line = {
@@ -304,7 +314,9 @@ def main_b200(a):
                        "build_s": round(build_s, 3), "ids_consistent_host_vs_device": ok,
                        "exchange": "none" if world == 1 else "NCCL all_gather of packed (I,D)[nq,k] + K4 merge kernel"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "scan_topk_kernel", "bytes_per_launch": launch_bytes,
+                         "traffic": None, "kernel": "scan_topk_kernel", "bytes_per_launch": launch_bytes, "scan_launches_per_step": scans_per_step,
+                         "note": "avg_launch_ms = CUDA-event time around the search on its stream / scan launches"
+                                 + (" (includes the ~2 us query-normalise kernel)" if normalize else ""),
                          "avg_launch_ms": scan_avg_ms, "peak_source": peak_src,
                          "whole_job_gbs": bytes_per_scan_total * scans_per_step / (total_ms / a.steps * 1e-3) / 1e9},
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12,

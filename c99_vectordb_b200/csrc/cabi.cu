@@ -76,7 +76,7 @@ struct b200_index {
     // options
     int64_t opt_variant = B200_SCAN_AUTO, opt_warps = 8, opt_stages = 0, opt_tile_rows = 0,
             opt_ctas_per_sm = 0, opt_evict_first = 0, opt_fullrank_min_k = B200_FUSED_K_MAX + 1,
-            opt_normalize_queries = 0, opt_qb = 0;
+            opt_normalize_queries = 0, opt_qb = 0, opt_dynamic = 1, opt_claim_chunk = 0, opt_fused_tail = -1;
     int64_t launches = 0;
 };
 
@@ -133,8 +133,8 @@ extern "C" int b200_index_create(b200_index** out, int d, int metric, int store,
     ix->num_sms = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ix->ticket, sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(ix->ticket, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ix->ticket, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(ix->ticket, 0, 2 * sizeof(unsigned int));
     if (e != cudaSuccess) {
         delete ix;
         return fail("index create: %s", cudaGetErrorString(e));
@@ -227,6 +227,9 @@ static const OptName kOpts[] = {
     {"scan_ctas_per_sm", &b200_index::opt_ctas_per_sm},
     {"scan_l2_evict_first", &b200_index::opt_evict_first},
     {"scan_query_block", &b200_index::opt_qb},
+    {"scan_dynamic_tiles", &b200_index::opt_dynamic},
+    {"scan_claim_chunk", &b200_index::opt_claim_chunk},
+    {"scan_fused_tail", &b200_index::opt_fused_tail},
     {"fullrank_min_k", &b200_index::opt_fullrank_min_k},
     {"normalize_queries", &b200_index::opt_normalize_queries},
 };
@@ -423,6 +426,15 @@ static ScanFn pick_scan(int metric, int store, int qb, int variant) {
     return nullptr;
 }
 
+typedef void (*MergeFn)(const ScanParams, uint32_t);
+static MergeFn pick_merge(int metric, int qb) {
+#define MG(M, Q) \
+    if (metric == M && qb == Q) return final_merge_kernel<M, Q>;
+    MG(0, 1) MG(0, 2) MG(0, 4) MG(0, 8) MG(1, 1) MG(1, 2) MG(1, 4) MG(1, 8)
+#undef MG
+    return nullptr;
+}
+
 static uint32_t next_pow2(uint32_t v) {
     uint32_t m = 1;
     while (m < v) m <<= 1;
@@ -436,7 +448,11 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
     const int kk = fullrank ? 1 : k;
     const size_t budget = ix->smem_optin - 1024;
     int variant = (int)ix->opt_variant;
-    if (variant == B200_SCAN_AUTO) variant = B200_VARIANT_BULK;
+    // AUTO (measured, profiles/r1_sweeps.md): the TMA-staged ring wins for fp32 rows of >= 3 KB
+    // (10M x 768: 7.39 TB/s vs 6.85); short rows and bf16 rows carry more instructions per byte and
+    // want the 32 resident warps/SM of the direct-load variant (d=384: 6.63 vs 6.05 TB/s).
+    if (variant == B200_SCAN_AUTO)
+        variant = (ix->store == B200_STORE_F32 && ix->pitch >= 3072) ? B200_VARIANT_BULK : B200_VARIANT_LDG;
     if (variant == B200_VARIANT_BULK) {
         int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_MAX / 32);
         bool ok = false;
@@ -457,7 +473,7 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
             size_t fixed_wo_scratch = fixed - (((size_t)scratch * 8 + 127) & ~(size_t)127);
             if (fixed_wo_scratch + 64 >= budget) continue;
             size_t avail = budget - fixed_wo_scratch - 64;
-            uint32_t stages = (uint32_t)std::min<uint64_t>(8, avail / ((uint64_t)nw * tile_bytes + (uint64_t)nw * 8));
+            uint32_t stages = (uint32_t)std::min<uint64_t>(8, avail / ((uint64_t)nw * tile_bytes + (uint64_t)nw * 12));
             if (ix->opt_stages > 0) stages = std::min<uint32_t>(stages, (uint32_t)ix->opt_stages);
             if (stages < 2) continue;
             size_t smem = scan_smem_bytes(B200_VARIANT_BULK, nw, qb, qstride, kk, fullrank, stages, (uint32_t)tile_bytes, scratch);
@@ -526,6 +542,16 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     p.nqb = nqb;
     p.k = score_keys ? 1 : k;
     p.ticket = ix->ticket;
+    p.dynamic = ix->opt_dynamic ? 1 : 0;
+    {
+        // one atomic claim hands out a run of tiles; keep >= ~16 claims per warp for balance
+        uint64_t tiles = ((uint64_t)ix->ntotal + pl.tile_rows - 1) / pl.tile_rows;
+        uint64_t per = tiles / ((uint64_t)pl.grid * pl.nw * 16);
+        p.claim_chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(per, 1), 16);
+        if (ix->opt_claim_chunk > 0) p.claim_chunk = (uint32_t)ix->opt_claim_chunk;
+    }
+    p.fused_tail = (nqb == 1 || score_keys) ? 1 : 0;
+    if (ix->opt_fused_tail >= 0) p.fused_tail = ix->opt_fused_tail ? 1 : 0;
     p.D = D;
     p.I = I;
     p.id_map = ix->ids_state == 1 ? ix->ids : nullptr;
@@ -547,6 +573,13 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     fn<<<pl.grid, pl.nw * 32, pl.smem, st>>>(p);
     ++ix->launches;
     CK(cudaGetLastError());
+    if (!score_keys && !p.fused_tail) {
+        MergeFn mf = pick_merge(ix->metric, pl.qb);
+        size_t msmem = (size_t)pl.scratch_keys * 8 + 16;
+        mf<<<nqb, 256, msmem, st>>>(p, (uint32_t)pl.grid);
+        ++ix->launches;
+        CK(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -42,7 +42,10 @@ struct ScanParams {
     int nqb;                  // queries in this launch (<= QB)
     int k;                    // results per query (top-k mode)
     uint64_t* partials;       // [grid, QB, k] per-CTA best keys
-    unsigned int* ticket;     // zero before launch; reset by the last CTA
+    unsigned int* ticket;     // [0] CTA-done ticket, [1] tile counter; zero before launch, reset by the last CTA
+    int dynamic;              // 1: tiles claimed in order from the global counter; 0: static striding
+    uint32_t claim_chunk;     // dynamic: consecutive tiles taken per atomic claim (>= 1)
+    int fused_tail;           // 1: the last CTA does the final merge; 0: final_merge_kernel follows
     float* D;                 // [nqb, k] out
     int64_t* I;               // [nqb, k] out
     const int64_t* id_map;    // row -> record id, or null
@@ -127,6 +130,88 @@ __device__ __forceinline__ void cta_bitonic_sort_desc(uint64_t* a, uint32_t m) {
     __syncthreads();
 }
 
+// Merge the per-CTA partial lists of query qi (nctas lists of k keys, each best-first) into the
+// final result, translate row -> record id (K5) and write D/I.  Whole CTA.  scratch[0..k) holds
+// the running best (sorted); whole CTA lists are appended behind it — unfiltered and without
+// atomics while no threshold exists yet, filtered against the running k-th best afterwards — and
+// the buffer is re-sorted when it fills up.
+template <int METRIC, int QB>
+__device__ __forceinline__ void final_merge_one(const ScanParams& p, int qi, uint32_t nctas, uint64_t* scratch,
+                                                unsigned int* sctr) {
+    const int k = p.k;
+    const uint32_t B = p.scratch_keys;
+    for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) scratch[i] = 0ull;
+    if (threadIdx.x == 0) *sctr = (unsigned)k;
+    __syncthreads();
+    uint32_t cta = 0;
+    while (cta < nctas) {
+        uint32_t filled = *sctr;
+        uint32_t fit = (B - filled) / (uint32_t)k;  // whole lists that fit (B >= 2k by construction)
+        if (fit == 0) fit = 1;
+        uint32_t take = nctas - cta < fit ? nctas - cta : fit;
+        uint64_t tau_now = scratch[k - 1];
+        __syncthreads();
+        if (tau_now == 0ull) {
+            for (uint32_t i = threadIdx.x; i < take * (uint32_t)k; i += blockDim.x) {
+                uint32_t c = cta + i / k, j = i % k;
+                scratch[filled + i] = __ldcg(p.partials + ((size_t)c * QB + qi) * k + j);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) *sctr = filled + take * (uint32_t)k;
+        } else {
+            for (uint32_t i = threadIdx.x; i < take * (uint32_t)k; i += blockDim.x) {
+                uint32_t c = cta + i / k, j = i % k;
+                uint64_t key = __ldcg(p.partials + ((size_t)c * QB + qi) * k + j);
+                if (key > tau_now) {
+                    unsigned slot = atomicAdd(sctr, 1u);
+                    scratch[slot] = key;
+                }
+            }
+        }
+        cta += take;
+        __syncthreads();
+        filled = *sctr;
+        bool last_round = (cta >= nctas);
+        bool full = (B - filled) < (uint32_t)k;
+        if (last_round || full) {
+            uint32_t mm = 2;
+            while (mm < filled) mm <<= 1;
+            for (uint32_t i = filled + threadIdx.x; i < mm; i += blockDim.x) scratch[i] = 0ull;
+            cta_bitonic_sort_desc(scratch, mm);
+            for (uint32_t i = (uint32_t)k + threadIdx.x; i < mm; i += blockDim.x) scratch[i] = 0ull;
+            __syncthreads();
+            if (threadIdx.x == 0) *sctr = (unsigned)k;
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        uint64_t key = scratch[i];
+        float dist;
+        int64_t id;
+        if (key == 0ull) {
+            dist = (METRIC == 0) ? -FLT_MAX : FLT_MAX;
+            id = -1;
+        } else {
+            dist = b200_key_score(key, METRIC);
+            uint32_t row = b200_key_row(key);
+            id = p.id_map ? p.id_map[row] : (int64_t)row + p.id_base;
+        }
+        p.D[(size_t)qi * k + i] = dist;
+        p.I[(size_t)qi * k + i] = id;
+    }
+    __syncthreads();
+}
+
+// One CTA per query: the final merge as its own launch, used when a scan launch carries several
+// queries (the fused last-CTA tail would merge them one after another).
+template <int METRIC, int QB>
+__global__ void __launch_bounds__(256) final_merge_kernel(const ScanParams p, uint32_t nctas) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem);
+    unsigned int* sctr = reinterpret_cast<unsigned int*>(smem + (size_t)p.scratch_keys * 8);
+    final_merge_one<METRIC, QB>(p, blockIdx.x, nctas, scratch, sctr);
+}
+
 // ---- the kernel --------------------------------------------------------------------------------
 template <int METRIC, int STORE, int QB, int RB, int VARIANT>
 __global__ void __launch_bounds__(B200_SCAN_THREADS_MAX)
@@ -139,7 +224,7 @@ scan_topk_kernel(const ScanParams p) {
     const int k = p.k;
 
     // ---- shared memory carve-up (host computes the same sizes: scan_smem_bytes) ----
-    // [ring: nw*stages*tile_bytes | scratch (aliases ring start)] [queries] [lists] [mbarriers] [ctr]
+    // [ring: nw*stages*tile_bytes | scratch (aliases ring start)] [queries] [lists] [mbarriers] [ctr] [stage tiles]
     uint32_t ring_bytes = (VARIANT == B200_VARIANT_BULK) ? nw * p.stages * p.tile_bytes : 0u;
     uint32_t scratch_bytes = p.scratch_keys * 8u;
     uint32_t region0 = ring_bytes > scratch_bytes ? ring_bytes : scratch_bytes;
@@ -152,6 +237,7 @@ scan_topk_kernel(const ScanParams p) {
     uint32_t list_bytes = fullrank ? 0u : (uint32_t)nw * QB * k * 8u;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + region0 + q_bytes + list_bytes);
     unsigned int* sctr = reinterpret_cast<unsigned int*>(bars + nw * (VARIANT == B200_VARIANT_BULK ? p.stages : 0u));
+    uint32_t* stage_tile = reinterpret_cast<uint32_t*>(sctr + 4) + warp * (VARIANT == B200_VARIANT_BULK ? p.stages : 0u);
     __shared__ unsigned int s_is_last;
 
     // ---- stage queries (zero padded) and clear lists ----
@@ -163,9 +249,27 @@ scan_topk_kernel(const ScanParams p) {
         for (int i = threadIdx.x; i < nw * QB * k; i += blockDim.x) lists[i] = 0ull;
 
     const uint32_t TR = p.tile_rows;
-    const uint64_t tiles_total = (p.n + TR - 1) / TR;
-    const uint64_t gw = (uint64_t)blockIdx.x * nw + warp;
-    const uint64_t GW = (uint64_t)gridDim.x * nw;
+    const uint32_t tiles_total = (uint32_t)((p.n + TR - 1) / TR);
+    const uint32_t NOTILE = 0xFFFFFFFFu;
+
+    // Tile scheduler.  dynamic: tiles are claimed in ascending order from one global counter, so
+    // every SM streams until the database is exhausted (no tail where the slow SMs finish alone)
+    // and DRAM sees one advancing front.  static: warp gw takes tiles gw, gw+GW, ...
+    uint32_t static_next = blockIdx.x * nw + warp;
+    const uint32_t static_step = gridDim.x * nw;
+    uint32_t chunk_next = 0, chunk_end = 0;  // lane 0: the claimed run of consecutive tiles
+    auto claim = [&]() -> uint32_t {  // called by lane 0 only
+        if (p.dynamic) {
+            if (chunk_next == chunk_end) {  // one atomic per claim_chunk tiles (a single hot address
+                chunk_next = atomicAdd(p.ticket + 1, p.claim_chunk);  // serialises at ~2.5 ns/op)
+                chunk_end = chunk_next + p.claim_chunk;
+            }
+            return chunk_next++;
+        }
+        uint32_t t = static_next;
+        static_next = (t > NOTILE - static_step) ? NOTILE : t + static_step;
+        return t;
+    };
 
     uint32_t bar0 = 0, ring0 = 0;
     uint64_t policy = 0;
@@ -180,8 +284,8 @@ scan_topk_kernel(const ScanParams p) {
     }
     __syncthreads();
 
-    auto issue = [&](uint32_t s, uint64_t t) {
-        uint64_t row0 = t * TR;
+    auto issue = [&](uint32_t s, uint32_t t) {
+        uint64_t row0 = (uint64_t)t * TR;
         uint64_t nr = p.n - row0 < TR ? p.n - row0 : TR;
         uint32_t bytes = (uint32_t)(nr * p.pitch_bytes);
         uint32_t bar = bar0 + 8u * s;
@@ -192,13 +296,28 @@ scan_topk_kernel(const ScanParams p) {
             bulk_g2s(ring0 + s * p.tile_bytes, p.rows + row0 * p.pitch_bytes, bytes, bar);
     };
 
+    uint32_t pending = NOTILE;  // lane 0: the tile claimed one step ahead (hides the atomic's latency)
+    uint32_t t_cur = NOTILE;    // LDG: the tile this warp works on
     if (VARIANT == B200_VARIANT_BULK) {
         if (lane == 0) {
             for (uint32_t s = 0; s < p.stages; ++s) {
-                uint64_t t = gw + (uint64_t)s * GW;
-                if (t < tiles_total) issue(s, t);
+                uint32_t t = claim();
+                if (t < tiles_total) {
+                    stage_tile[s] = t;
+                    issue(s, t);
+                } else {
+                    stage_tile[s] = NOTILE;
+                }
             }
+            pending = claim();
         }
+        __syncwarp();
+    } else {
+        if (lane == 0) {
+            t_cur = claim();
+            pending = claim();
+        }
+        t_cur = __shfl_sync(B200_FULL_MASK, t_cur, 0);
     }
 
     uint64_t tau[QB];
@@ -213,18 +332,23 @@ scan_topk_kernel(const ScanParams p) {
     const int qstride4 = p.qstride >> 2;
     const uint32_t nvec = p.nvec;
 
-    uint32_t it = 0;
-    for (uint64_t t = gw; t < tiles_total; t += GW, ++it) {
-        const uint64_t tile_row0 = t * TR;
-        const uint32_t rows_in_tile = (uint32_t)(p.n - tile_row0 < TR ? p.n - tile_row0 : TR);
+    for (uint32_t it = 0;; ++it) {
         uint32_t s = 0;
         const uint8_t* tile_smem = nullptr;
+        uint32_t t;
         if (VARIANT == B200_VARIANT_BULK) {
             s = it % p.stages;
+            t = stage_tile[s];
+            if (t == NOTILE) break;
             uint32_t parity = (it / p.stages) & 1u;
             mbar_wait(bar0 + 8u * s, parity);
             tile_smem = ring + ((size_t)warp * p.stages + s) * p.tile_bytes;
+        } else {
+            t = t_cur;
+            if (t >= tiles_total) break;
         }
+        const uint64_t tile_row0 = (uint64_t)t * TR;
+        const uint32_t rows_in_tile = (uint32_t)(p.n - tile_row0 < TR ? p.n - tile_row0 : TR);
         for (uint32_t g = 0; g < rows_in_tile; g += RB) {
             float acc[QB][RB];
 #pragma unroll
@@ -296,19 +420,30 @@ scan_topk_kernel(const ScanParams p) {
             }
         }
         if (VARIANT == B200_VARIANT_BULK) {
+            __syncwarp();  // every lane has finished reading this stage
+            if (lane == 0) {
+                uint32_t tn = pending;
+                if (tn < tiles_total) {
+                    stage_tile[s] = tn;
+                    issue(s, tn);
+                    pending = claim();
+                } else {
+                    stage_tile[s] = NOTILE;
+                }
+            }
             __syncwarp();
-            uint64_t tn = t + (uint64_t)p.stages * GW;
-            if (lane == 0 && tn < tiles_total) issue(s, tn);
+        } else {
+            uint32_t tn = pending;
+            if (lane == 0 && tn < tiles_total) pending = claim();
+            t_cur = __shfl_sync(B200_FULL_MASK, tn, 0);
         }
     }
-
-    if (fullrank) return;
 
     // ---- CTA merge: the warps' lists -> this CTA's best k per query ----
     __syncthreads();  // all warps done; every issued bulk copy has been consumed
     uint32_t m = 2;
     while (m < (uint32_t)(nw * k)) m <<= 1;
-    for (int qi = 0; qi < p.nqb; ++qi) {
+    for (int qi = 0; qi < (fullrank ? 0 : p.nqb); ++qi) {
         for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
             uint64_t v = 0ull;
             if (i < (uint32_t)(nw * k)) {
@@ -333,64 +468,12 @@ scan_topk_kernel(const ScanParams p) {
     __syncthreads();
     if (!s_is_last) return;
     __threadfence();
-    for (int qi = 0; qi < p.nqb; ++qi) {
-        // scratch[0..k) holds the running best (sorted); whole CTA lists are appended behind it,
-        // filtered against the running k-th best, and the buffer is re-sorted when it fills up.
-        for (uint32_t i = threadIdx.x; i < p.scratch_keys; i += blockDim.x) scratch[i] = 0ull;
-        if (threadIdx.x == 0) *sctr = (unsigned)k;
-        __syncthreads();
-        const uint32_t B = p.scratch_keys;
-        uint32_t cta = 0;
-        while (cta < gridDim.x) {
-            // how many whole CTA lists fit in the free part of the buffer
-            uint32_t filled = *sctr;
-            uint32_t fit = (B - filled) / (uint32_t)k;
-            if (fit == 0) fit = 1;  // cannot happen: B >= 2k is guaranteed by the host
-            uint32_t take = gridDim.x - cta < fit ? gridDim.x - cta : fit;
-            uint64_t tau_now = scratch[k - 1];
-            __syncthreads();
-            for (uint32_t i = threadIdx.x; i < take * (uint32_t)k; i += blockDim.x) {
-                uint32_t c = cta + i / k, j = i % k;
-                uint64_t key = __ldcg(p.partials + ((size_t)c * QB + qi) * k + j);
-                if (key > tau_now) {
-                    unsigned slot = atomicAdd(sctr, 1u);
-                    scratch[slot] = key;
-                }
-            }
-            cta += take;
-            __syncthreads();
-            filled = *sctr;
-            bool last_round = (cta >= gridDim.x);
-            bool full = (B - filled) < (uint32_t)k;
-            if (last_round || full) {
-                uint32_t mm = 2;
-                while (mm < filled) mm <<= 1;
-                for (uint32_t i = filled + threadIdx.x; i < mm; i += blockDim.x) scratch[i] = 0ull;
-                cta_bitonic_sort_desc(scratch, mm);
-                for (uint32_t i = (uint32_t)k + threadIdx.x; i < mm; i += blockDim.x) scratch[i] = 0ull;
-                __syncthreads();
-                if (threadIdx.x == 0) *sctr = (unsigned)k;
-                __syncthreads();
-            }
-        }
-        for (int i = threadIdx.x; i < k; i += blockDim.x) {
-            uint64_t key = scratch[i];
-            float dist;
-            int64_t id;
-            if (key == 0ull) {
-                dist = (METRIC == 0) ? -FLT_MAX : FLT_MAX;
-                id = -1;
-            } else {
-                dist = b200_key_score(key, METRIC);
-                uint32_t row = b200_key_row(key);
-                id = p.id_map ? p.id_map[row] : (int64_t)row + p.id_base;
-            }
-            p.D[(size_t)qi * k + i] = dist;
-            p.I[(size_t)qi * k + i] = id;
-        }
-        __syncthreads();
+    if (!fullrank && p.fused_tail)
+        for (int qi = 0; qi < p.nqb; ++qi) final_merge_one<METRIC, QB>(p, qi, gridDim.x, scratch, sctr);
+    if (threadIdx.x == 0) {  // ready for the next launch on this stream
+        p.ticket[0] = 0u;
+        p.ticket[1] = 0u;
     }
-    if (threadIdx.x == 0) *p.ticket = 0u;  // ready for the next launch on this stream
 }
 
 // shared memory the kernel needs for a configuration (host side twin of the carve-up above)
@@ -402,6 +485,6 @@ static inline size_t scan_smem_bytes(int variant, int nw, int QB, int qstride, i
     region0 = (region0 + 127) & ~(size_t)127;
     size_t q = (size_t)QB * qstride * 4;
     size_t lists = fullrank ? 0 : (size_t)nw * QB * k * 8;
-    size_t bars = variant == B200_VARIANT_BULK ? (size_t)nw * stages * 8 : 0;
+    size_t bars = variant == B200_VARIANT_BULK ? (size_t)nw * stages * (8 + 4) : 0;  // mbarriers + stage tiles
     return region0 + q + lists + bars + 16;
 }

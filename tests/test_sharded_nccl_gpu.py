@@ -1,0 +1,72 @@
+"""Real multi-GPU run of the row-sharded index (NCCL all-gather + K4 merge kernel).  Needs >= 2
+GPUs (gpurun --gpus 2); on a 1-GPU box the test is skipped — the host logic is covered on CPU by
+tests/test_sharded_gloo_cpu.py."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    from oracle import oracle
+    from c99_vectordb_b200.sharded import ShardedIndexFlat
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        for metric, n, d, k, nq in ((0, 200_003, 384, 10, 1), (1, 50_000, 768, 100, 5), (1, 7, 16, 5, 2)):
+            base = oracle.synth_rows(n // 2, d, 9)
+            db = np.concatenate([base, base, oracle.synth_rows(n - 2 * (n // 2), d, 10)])  # cross-shard exact ties
+            ids = np.arange(n, dtype=np.int64) * 3 + 5
+            q = oracle.synth_rows(nq, d, 8)
+            idx = ShardedIndexFlat(d, metric)
+            idx.add_with_ids(db, ids)
+            D, I = idx.search(q, k)
+            Dw, Iw = oracle.search(metric, db, q, k, ids=ids, order=oracle.ORDER_DEVICE)
+            np.testing.assert_array_equal(I, Iw)
+            np.testing.assert_array_equal(D, Dw)
+        # device-generated shards: global ids are global row positions
+        idx = ShardedIndexFlat(384, 1)
+        idx.add_synthetic(300_000, 1234)
+        q = oracle.synth_rows(3, 384, 5678)
+        D, I = idx.search(q, 10)
+        Dw, Iw = oracle.search(1, oracle.synth_rows(300_000, 384, 1234), q, 10, order=oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)
+        np.save(os.path.join(out_dir, f"ok_{rank}.npy"), I)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_nccl_matches_unsharded_oracle(tmp_path, gpu):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [np.load(tmp_path / f"ok_{r}.npy") for r in range(world)]
+    for o in outs[1:]:
+        np.testing.assert_array_equal(o, outs[0])
