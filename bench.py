@@ -42,6 +42,7 @@ WORKLOADS = {
     "100Mx384_l2_f32_k10_nq1": (100_000_000, 384, 1, "f32", False, 10, 1),
     "10Mx1024_cos_bf16_k10_nq1": (10_000_000, 1024, 0, "bf16", True, 10, 1),
     "10kx384_ip_f32_k10_nq100": (10_000, 384, 0, "f32", True, 10, 100),
+    "10Mx768_ip_f32_k100_nq10000": (10_000_000, 768, 0, "f32", False, 100, 10_000),  # config 2: tcgen05 batched path
 }
 DEFAULT_WORKLOAD = "10Mx768_ip_f32_k10_nq1"
 DB_SEED, Q_SEED = 1234, 5678
@@ -55,6 +56,17 @@ def scan_passes(nq: int) -> int:
         rem -= min(qb, rem)
         passes += 1
     return passes
+
+
+def measured_tensor_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            j = json.loads(p.read_text())
+            return float(j["bf16_tflops_sustained"]), "measured sustained bf16 (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 1400.0, "fallback (B200_PROFILING.md)"
 
 
 def measured_peaks():
@@ -299,6 +311,7 @@ def main_b200(a):
 
     if rank == 0:
         peak, peak_src = measured_peaks()
+        gemm_used = bool(base.get_option("stat_gemm_used"))
         launch_bytes = (hi - lo) * d * elem  # algorithmic bytes one scan launch streams on this rank
         scans_per_step = scan_passes(nq)  # nq > 8 -> several passes over the database per step
         scan_avg_ms = scan_avg_ms / scans_per_step
@@ -324,6 +337,20 @@ def main_b200(a):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if gemm_used:
+            # batched path: the dominant kernel is the tcgen05 emit pass; algorithmic flops = 2 nq N d
+            p2_ms = base.get_option("stat_gemm_pass2_us") / 1e3
+            flops = 2.0 * nq * (hi - lo) * d
+            tpeak, tsrc = measured_tensor_peak()
+            line["roofline"] = {"bound": "tensor", "achieved": flops / (p2_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                                "frac": flops / (p2_ms * 1e-3) / 1e12 / tpeak, "traffic": None, "kernel": "gemm_topk_kernel (emit pass)",
+                                "flops_per_launch": flops, "avg_launch_ms": p2_ms, "peak_source": tsrc,
+                                "pass1_ms": base.get_option("stat_gemm_pass1_us") / 1e3,
+                                "rerank_ms": base.get_option("stat_gemm_rerank_us") / 1e3,
+                                "uncertified_queries_recomputed": base.get_option("stat_gemm_fallbacks"),
+                                "candidates_per_query": base.get_option("stat_gemm_cand_total") / nq,
+                                "note": "bf16 tensor-core pass (tcgen05, TMEM accumulators) + exact fp32 re-rank; "
+                                        "launch time is the kernel's own CUDA-event bracket from the last step"}
         if world == 1 and not a.no_cpu:
             cb1 = run_cpu(a.workload, 3, 1, rowpar=False)
             cbN = run_cpu(a.workload, 8, 1, rowpar=True)

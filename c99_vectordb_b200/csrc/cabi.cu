@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "fullrank.cuh"
+#include "gemm_topk.cuh"
 #include "merge.cuh"
 #include "rows.cuh"
 #include "scan_topk.cuh"
@@ -77,6 +78,24 @@ struct b200_index {
     int64_t opt_variant = B200_SCAN_AUTO, opt_warps = 8, opt_stages = 0, opt_tile_rows = 0,
             opt_ctas_per_sm = 0, opt_evict_first = 0, opt_fullrank_min_k = B200_FUSED_K_MAX + 1,
             opt_normalize_queries = 0, opt_qb = 0, opt_dynamic = 1, opt_claim_chunk = 0, opt_fused_tail = -1;
+    int64_t opt_gemm_min_nq = 64, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 64, opt_gemm_sample_tiles = 1024;
+    // read-only statistics of the last batched (K3) search
+    int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
+            stat_gemm_pass2_us = 0, stat_gemm_rerank_us = 0;
+    // K3 state
+    __nv_bfloat16* sh_rows = nullptr;  // bf16 shadow of the rows [ntotal, kpad]
+    float* sh_norm2 = nullptr;
+    unsigned int* sh_maxnorm = nullptr;
+    int64_t sh_valid_rows = -1;        // rows covered by the shadow (-1 = none)
+    size_t sh_cap_rows = 0;
+    __nv_bfloat16* g_qb = nullptr;     // bf16 queries [m_tiles*128, kpad]
+    float* g_qnorm2 = nullptr;
+    float* g_tilemax = nullptr;
+    float* g_theta = nullptr;
+    unsigned int* g_count = nullptr;
+    uint32_t* g_cand = nullptr;
+    int* g_cert = nullptr;
+    size_t g_qb_cap = 0, g_q_cap = 0, g_tilemax_cap = 0, g_cand_cap = 0;
     int64_t launches = 0;
 };
 
@@ -159,6 +178,16 @@ extern "C" int b200_index_destroy(b200_index* ix) {
     cudaFree(ix->fr_hi);
     for (int i = 0; i < 4; ++i) cudaFree(ix->fr_buf[i]);
     cudaFree(ix->fr_hist);
+    cudaFree(ix->sh_rows);
+    cudaFree(ix->sh_norm2);
+    cudaFree(ix->sh_maxnorm);
+    cudaFree(ix->g_qb);
+    cudaFree(ix->g_qnorm2);
+    cudaFree(ix->g_tilemax);
+    cudaFree(ix->g_theta);
+    cudaFree(ix->g_count);
+    cudaFree(ix->g_cand);
+    cudaFree(ix->g_cert);
     if (ix->pin) cudaFreeHost(ix->pin);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -171,6 +200,7 @@ extern "C" int b200_index_reset(b200_index* ix) {
     CK(cudaStreamSynchronize(ix->stream));
     ix->ntotal = 0;
     ix->ids_state = 0;
+    ix->sh_valid_rows = -1;
     return 0;
 }
 
@@ -230,6 +260,16 @@ static const OptName kOpts[] = {
     {"scan_dynamic_tiles", &b200_index::opt_dynamic},
     {"scan_claim_chunk", &b200_index::opt_claim_chunk},
     {"scan_fused_tail", &b200_index::opt_fused_tail},
+    {"gemm_min_nq", &b200_index::opt_gemm_min_nq},
+    {"gemm_emit_factor", &b200_index::opt_gemm_emit_factor},
+    {"gemm_chunk_tiles", &b200_index::opt_gemm_chunk_tiles},
+    {"gemm_sample_tiles", &b200_index::opt_gemm_sample_tiles},
+    {"stat_gemm_used", &b200_index::stat_gemm_used},
+    {"stat_gemm_fallbacks", &b200_index::stat_gemm_fallbacks},
+    {"stat_gemm_cand_total", &b200_index::stat_gemm_cand_total},
+    {"stat_gemm_pass1_us", &b200_index::stat_gemm_pass1_us},
+    {"stat_gemm_pass2_us", &b200_index::stat_gemm_pass2_us},
+    {"stat_gemm_rerank_us", &b200_index::stat_gemm_rerank_us},
     {"fullrank_min_k", &b200_index::opt_fullrank_min_k},
     {"normalize_queries", &b200_index::opt_normalize_queries},
 };
@@ -332,6 +372,7 @@ static int add_common(b200_index* ix, const float* x, bool x_is_dev, int64_t n, 
     }
     CK(cudaStreamSynchronize(st));
     ix->ntotal += n;
+    ix->sh_valid_rows = -1;
     return 0;
 }
 
@@ -399,6 +440,7 @@ extern "C" int b200_index_add_synthetic(b200_index* ix, int64_t n, uint64_t seed
     }
     CK(cudaStreamSynchronize(st));
     ix->ntotal += n;
+    ix->sh_valid_rows = -1;
     return 0;
 }
 
@@ -627,6 +669,254 @@ static int pick_qb(int64_t remaining, int64_t forced) {
     return 1;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K3: batched search on the tensor cores (gemm_topk.cuh)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int get_encode_fn(EncodeTiledFn* out) {
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) return fail("cuTensorMapEncodeTiled is not available from the driver");
+        cached = (EncodeTiledFn)fn;
+    }
+    *out = cached;
+    return 0;
+}
+// bf16 K-major matrix [rows, kpad] -> 2-D tensor map with a {64, box_rows} box and 128-byte swizzle
+static int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint32_t kpad, uint32_t box_rows) {
+    EncodeTiledFn enc = nullptr;
+    CKI(get_encode_fn(&enc));
+    cuuint64_t gdim[2] = {kpad, rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)kpad * 2};
+    cuuint32_t box[2] = {G3_BLOCK_K, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+static bool gemm_eligible(b200_index* ix, int64_t nq, int64_t k) {
+    return ix->opt_gemm_min_nq > 0 && nq >= ix->opt_gemm_min_nq && ix->metric == B200_METRIC_IP && k <= B200_FUSED_K_MAX &&
+           ix->ntotal >= 65536 && ix->ntotal >= 512 * k && ix->d >= 32 && k < ix->opt_fullrank_min_k;
+}
+
+static int ensure_shadow(b200_index* ix, cudaStream_t st) {
+    const int kpad = (ix->d + G3_BLOCK_K - 1) / G3_BLOCK_K * G3_BLOCK_K;
+    if (ix->sh_valid_rows == ix->ntotal) return 0;
+    if (ix->sh_cap_rows < (size_t)ix->ntotal) {
+        CK(cudaStreamSynchronize(st));
+        if (ix->sh_rows) CK(cudaFree(ix->sh_rows));
+        if (ix->sh_norm2) CK(cudaFree(ix->sh_norm2));
+        ix->sh_rows = nullptr;
+        ix->sh_norm2 = nullptr;
+        ix->sh_cap_rows = 0;
+        size_t cap = (size_t)std::max<int64_t>(ix->ntotal, ix->capacity);
+        cudaError_t e = cudaMalloc((void**)&ix->sh_rows, cap * kpad * sizeof(__nv_bfloat16));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail("cannot allocate the %.2f GB bf16 shadow for batched search: %s", (double)cap * kpad * 2 / 1e9,
+                        cudaGetErrorString(e));
+        }
+        CK(cudaMalloc((void**)&ix->sh_norm2, cap * sizeof(float)));
+        ix->sh_cap_rows = cap;
+    }
+    if (!ix->sh_maxnorm) CK(cudaMalloc((void**)&ix->sh_maxnorm, sizeof(unsigned int)));
+    CK(cudaMemsetAsync(ix->sh_maxnorm, 0, sizeof(unsigned int), st));
+    shadow_rows_kernel<<<ix->num_sms * 8, 256, 0, st>>>(ix->rows, ix->pitch, ix->store, (uint64_t)ix->ntotal, ix->d, kpad,
+                                                        ix->sh_rows, ix->sh_norm2, ix->sh_maxnorm);
+    ++ix->launches;
+    CK(cudaGetLastError());
+    ix->sh_valid_rows = ix->ntotal;
+    return 0;
+}
+
+static int search_scan_block(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev, int64_t* I_dev,
+                             cudaStream_t st);
+
+static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev, int64_t* I_dev,
+                       cudaStream_t st) {
+    const int kpad = (ix->d + G3_BLOCK_K - 1) / G3_BLOCK_K * G3_BLOCK_K;
+    const uint64_t n = (uint64_t)ix->ntotal;
+    const uint32_t NT = (uint32_t)((n + G3_BLOCK_N - 1) / G3_BLOCK_N);
+    const uint32_t m_tiles = (uint32_t)((nq + G3_BLOCK_M - 1) / G3_BLOCK_M);
+    const uint32_t cap = 4096;
+    CKI(ensure_shadow(ix, st));
+    // ---- scratch ----
+    const size_t qb_elems = (size_t)m_tiles * G3_BLOCK_M * kpad;
+    // sampled tiles: each contributes 8 group maxima; at most 8192 maxima per query are sorted
+    const uint32_t T = (uint32_t)std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(ix->opt_gemm_sample_tiles, 64), 1024), NT);
+    const uint32_t stride = std::max<uint32_t>(1, NT / T);
+    if (ix->g_qb_cap < qb_elems || ix->g_q_cap < (size_t)nq || ix->g_tilemax_cap < (size_t)nq * T * 8 ||
+        ix->g_cand_cap < (size_t)nq * cap)
+        CK(cudaStreamSynchronize(st));
+    CKI(grow(&ix->g_qb, &ix->g_qb_cap, qb_elems));
+    if (ix->g_q_cap < (size_t)nq) {
+        cudaFree(ix->g_qnorm2); cudaFree(ix->g_theta); cudaFree(ix->g_count); cudaFree(ix->g_cert);
+        ix->g_qnorm2 = nullptr; ix->g_theta = nullptr; ix->g_count = nullptr; ix->g_cert = nullptr;
+        ix->g_q_cap = 0;
+        CK(cudaMalloc((void**)&ix->g_qnorm2, (size_t)nq * 4));
+        CK(cudaMalloc((void**)&ix->g_theta, (size_t)nq * 4));
+        CK(cudaMalloc((void**)&ix->g_count, (size_t)nq * 4));
+        CK(cudaMalloc((void**)&ix->g_cert, (size_t)nq * 4));
+        ix->g_q_cap = (size_t)nq;
+    }
+    CKI(grow(&ix->g_tilemax, &ix->g_tilemax_cap, (size_t)nq * T * 8));
+    CKI(grow(&ix->g_cand, &ix->g_cand_cap, (size_t)nq * cap));
+    // ---- query shadow (zero padded to whole 128-query tiles) ----
+    CK(cudaMemsetAsync(ix->g_qb, 0, qb_elems * sizeof(__nv_bfloat16), st));
+    shadow_rows_kernel<<<(unsigned)std::min<int64_t>((nq + 7) / 8, ix->num_sms * 8), 256, 0, st>>>(
+        (const uint8_t*)q_dev, (uint64_t)ix->d * 4, 0, (uint64_t)nq, ix->d, kpad, ix->g_qb, ix->g_qnorm2, nullptr);
+    ++ix->launches;
+    CK(cudaGetLastError());
+    CUtensorMap tm_q, tm_db;
+    CKI(make_tmap_bf16(&tm_q, ix->g_qb, (uint64_t)m_tiles * G3_BLOCK_M, (uint32_t)kpad, G3_BLOCK_M));
+    CKI(make_tmap_bf16(&tm_db, ix->sh_rows, n, (uint32_t)kpad, G3_BLOCK_N));
+    CK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM_BYTES));
+    cudaEvent_t ev[4];
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    GemmParams gp;
+    memset(&gp, 0, sizeof gp);
+    gp.nq = (uint32_t)nq;
+    gp.m_tiles = m_tiles;
+    gp.n = n;
+    gp.k_blocks = (uint32_t)(kpad / G3_BLOCK_K);
+    gp.chunk_tiles = (uint32_t)std::max<int64_t>(1, ix->opt_gemm_chunk_tiles);
+    gp.theta = ix->g_theta;
+    gp.cand_count = ix->g_count;
+    gp.cand_rows = ix->g_cand;
+    gp.cand_cap = cap;
+    gp.tilemax = ix->g_tilemax;
+    // ---- pass 1: tile maxima over a strided sample of T tiles -> theta ----
+    gp.mode = G3_MODE_TILEMAX;
+    gp.tile_first = 0;
+    gp.tile_stride = stride;
+    gp.tile_count = T;
+    CK(cudaEventRecord(ev[0], st));
+    gemm_topk_kernel<<<ix->num_sms, G3_THREADS, G3_SMEM_BYTES, st>>>(tm_q, tm_db, gp);
+    ++ix->launches;
+    CK(cudaGetLastError());
+    {
+        // expected emissions per query = emit_factor * k.  The rank-th largest of the sampled
+        // 32-row group maxima estimates the score quantile (sample rows / n) * that count; the rank
+        // is kept below G/8 so that two of the top scores rarely share a group.
+        const uint32_t G = T * 8;
+        double sample_rows = (double)T * G3_BLOCK_N;
+        double want = (double)std::max<int64_t>(ix->opt_gemm_emit_factor, 2) * (double)k;
+        double r = want * std::min(1.0, sample_rows / (double)n);
+        uint32_t rank = (uint32_t)std::min<double>(std::max(r, 8.0), (double)(G / 8));
+        uint32_t m = 2;
+        while (m < G) m <<= 1;
+        select_theta_kernel<<<(unsigned)nq, 256, (size_t)m * 4, st>>>(ix->g_tilemax, G, rank, ix->g_theta);
+        ++ix->launches;
+        CK(cudaGetLastError());
+    }
+    // ---- pass 2: emit candidates over every tile ----
+    CK(cudaMemsetAsync(ix->g_count, 0, (size_t)nq * 4, st));
+    gp.mode = G3_MODE_EMIT;
+    gp.tile_stride = 1;
+    gp.tile_count = NT;
+    CK(cudaEventRecord(ev[1], st));
+    gemm_topk_kernel<<<ix->num_sms, G3_THREADS, G3_SMEM_BYTES, st>>>(tm_q, tm_db, gp);
+    ++ix->launches;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev[2], st));
+    // ---- exact re-rank + certificate ----
+    RerankParams rp;
+    memset(&rp, 0, sizeof rp);
+    rp.rows = ix->rows;
+    rp.pitch_bytes = ix->pitch;
+    rp.nvec = (uint32_t)(ix->pitch / 16);
+    rp.store = ix->store;
+    rp.d = ix->d;
+    rp.qstride = (ix->d_pad + 7) / 8 * 8;
+    rp.q = q_dev;
+    rp.cand_rows = ix->g_cand;
+    rp.cand_count = ix->g_count;
+    rp.cand_cap = cap;
+    rp.theta = ix->g_theta;
+    rp.qnorm2 = ix->g_qnorm2;
+    rp.max_norm2_bits = ix->sh_maxnorm;
+    // |approx - exact| <= (2u + u^2) |q||y| with u = 2^-8 (two bf16 roundings), plus fp32 accumulation
+    // slack on both sides (d * 2^-22 each, generous)
+    rp.eps_rel = 0.0078278f + 2.0f * (float)ix->d * 2.4e-7f + 1e-4f;
+    rp.n = n;
+    rp.k = (int)k;
+    rp.id_map = ix->ids_state == 1 ? ix->ids : nullptr;
+    rp.D = D_dev;
+    rp.I = I_dev;
+    rp.certified = ix->g_cert;
+    const size_t rsmem = (size_t)rp.qstride * 4 + (size_t)cap * 8;
+    CK(cudaFuncSetAttribute(rerank_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    rerank_kernel<0><<<(unsigned)nq, 256, rsmem, st>>>(rp);
+    ++ix->launches;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev[3], st));
+    // ---- uncertified queries go through the exact scan ----
+    std::vector<int> cert((size_t)nq);
+    std::vector<unsigned int> counts((size_t)nq);
+    CK(cudaMemcpyAsync(cert.data(), ix->g_cert, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(counts.data(), ix->g_count, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); ix->stat_gemm_pass1_us = (int64_t)(ms * 1e3);
+    CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); ix->stat_gemm_pass2_us = (int64_t)(ms * 1e3);
+    CK(cudaEventElapsedTime(&ms, ev[2], ev[3])); ix->stat_gemm_rerank_us = (int64_t)(ms * 1e3);
+    for (auto& e : ev) cudaEventDestroy(e);
+    std::vector<int64_t> bad;
+    int64_t cand_total = 0;
+    for (int64_t i = 0; i < nq; ++i) {
+        cand_total += counts[(size_t)i];
+        if (!cert[(size_t)i]) bad.push_back(i);
+    }
+    ix->stat_gemm_used = 1;
+    ix->stat_gemm_fallbacks = (int64_t)bad.size();
+    ix->stat_gemm_cand_total = cand_total;
+    if (!bad.empty()) {
+        // gather the failed queries, search them exactly 8 at a time, scatter the results back
+        const size_t nb = bad.size();
+        float* qtmp = nullptr; float* Dtmp = nullptr; int64_t* Itmp = nullptr;
+        CK(cudaMalloc((void**)&qtmp, nb * ix->d * 4));
+        CK(cudaMalloc((void**)&Dtmp, nb * (size_t)k * 4));
+        CK(cudaMalloc((void**)&Itmp, nb * (size_t)k * 8));
+        for (size_t j = 0; j < nb; ++j)
+            CK(cudaMemcpyAsync(qtmp + j * ix->d, q_dev + (size_t)bad[j] * ix->d, (size_t)ix->d * 4, cudaMemcpyDeviceToDevice, st));
+        int rc = search_scan_block(ix, qtmp, (int64_t)nb, k, Dtmp, Itmp, st);
+        if (rc == 0)
+            for (size_t j = 0; j < nb; ++j) {
+                cudaMemcpyAsync(D_dev + (size_t)bad[j] * k, Dtmp + j * k, (size_t)k * 4, cudaMemcpyDeviceToDevice, st);
+                cudaMemcpyAsync(I_dev + (size_t)bad[j] * k, Itmp + j * k, (size_t)k * 8, cudaMemcpyDeviceToDevice, st);
+            }
+        cudaStreamSynchronize(st);
+        cudaFree(qtmp); cudaFree(Dtmp); cudaFree(Itmp);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+
+static int search_scan_block(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev, int64_t* I_dev,
+                             cudaStream_t st) {
+    int64_t q0 = 0;
+    while (q0 < nq) {
+        int qb = pick_qb(nq - q0, ix->opt_qb);
+        int nqb = (int)std::min<int64_t>(qb, nq - q0);
+        ScanPlan pl;
+        CKI(plan_scan(ix, qb, (int)k, false, &pl));
+        CKI(launch_scan(ix, pl, q_dev + (size_t)q0 * ix->d, nqb, (int)k, D_dev + (size_t)q0 * k, I_dev + (size_t)q0 * k,
+                        nullptr, st));
+        q0 += nqb;
+    }
+    return 0;
+}
+
 extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev,
                                      int64_t* I_dev, void* stream) {
     if (!ix) return fail("null index");
@@ -658,18 +948,17 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
         q_dev = ix->qn_dev;
     }
     const bool fullrank = k >= ix->opt_fullrank_min_k || k > B200_FUSED_K_MAX;
+    ix->stat_gemm_used = 0;
     if (!fullrank) {
-        int64_t q0 = 0;
-        while (q0 < nq) {
-            int qb = pick_qb(nq - q0, ix->opt_qb);
-            int nqb = (int)std::min<int64_t>(qb, nq - q0);
-            ScanPlan pl;
-            CKI(plan_scan(ix, qb, (int)k, false, &pl));
-            CKI(launch_scan(ix, pl, q_dev + (size_t)q0 * ix->d, nqb, (int)k, D_dev + (size_t)q0 * k,
-                            I_dev + (size_t)q0 * k, nullptr, st));
-            q0 += nqb;
+        if (gemm_eligible(ix, nq, k)) {
+            // K3 in blocks of at most 16384 queries (bounds the candidate scratch)
+            for (int64_t q0 = 0; q0 < nq; q0 += 16384) {
+                int64_t nb = std::min<int64_t>(16384, nq - q0);
+                CKI(search_gemm(ix, q_dev + (size_t)q0 * ix->d, nb, k, D_dev + (size_t)q0 * k, I_dev + (size_t)q0 * k, st));
+            }
+            return 0;
         }
-        return 0;
+        return search_scan_block(ix, q_dev, nq, k, D_dev, I_dev, st);
     }
     // full ranking: scores for a block of queries, then one stable radix sort per query
     const uint64_t n = (uint64_t)ix->ntotal;

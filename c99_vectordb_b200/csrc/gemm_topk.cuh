@@ -1,0 +1,470 @@
+// gemm_topk.cuh — K3: batched queries as a dense contraction on the 5th-gen tensor cores.
+//
+// Replaces index.search(x[nq,d], k) for large nq (memo_cli.py:292; faiss's BLAS path for nq >= 20
+// [upstream]).  10k queries x 10M rows x 768 is 1.5e14 flop: tensor-core work, not a GEMV.
+//
+// tcgen05 has no fp32 input kind, so one tensor-core pass cannot give fp32-exact ids.  The path is
+// therefore "approximate, then prove":
+//   1. shadow copies: rows and queries rounded to bf16 (K-major), row/query norms kept in fp32.
+//   2. THIS kernel: S' = Q' * DB'^T tile by tile (UMMA 128 x 256 x 16, accumulators in TMEM,
+//      operands staged by TMA with 128-byte swizzle through a 4-stage mbarrier ring), with a fused
+//      epilogue that never writes scores to HBM:
+//        MODE_TILEMAX : max score per (query, 32-row group) over a strided sample of tiles — used
+//                       to pick each query's emission threshold theta;
+//        MODE_EMIT    : rows whose approximate score exceeds theta[query] are appended to the
+//                       query's candidate list (expected ~1e-4 of all scores).
+//   3. rerank kernel: exact fp32 scores of the candidates with the SAME arithmetic as the scan
+//      kernel (bit-identical to the nq < 20 path), top-k under the tie rule, and a certificate:
+//      every row not emitted has exact score <= theta + eps (eps = proven bf16 rounding bound), so
+//      the result is exact iff the k-th best exact score beats theta + eps.  Uncertified queries
+//      are re-run through the exact scan kernel.
+//
+// Warp roles (6 warps): 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..5 = epilogue
+// (warp w reads TMEM lanes 32*(w%4)..+31: one query per thread).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+#define G3_BLOCK_M 128
+#define G3_BLOCK_N 256
+#define G3_BLOCK_K 64   // bf16 elements = 128 bytes = one swizzle atom row
+#define G3_UMMA_K 16
+#define G3_STAGES 4
+#define G3_THREADS 192
+#define G3_A_BYTES (G3_BLOCK_M * G3_BLOCK_K * 2)
+#define G3_B_BYTES (G3_BLOCK_N * G3_BLOCK_K * 2)
+#define G3_STAGE_BYTES (G3_A_BYTES + G3_B_BYTES)
+#define G3_SMEM_BYTES (G3_STAGES * G3_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+#define G3_MODE_TILEMAX 0
+#define G3_MODE_EMIT 1
+
+struct GemmParams {
+    uint32_t nq;            // real queries
+    uint32_t m_tiles;       // ceil(nq / 128)
+    uint64_t n;             // database rows
+    uint32_t k_blocks;      // d_pad64 / 64
+    uint32_t tile_first;    // first 256-row tile of this pass
+    uint32_t tile_stride;   // tile step (sampling)
+    uint32_t tile_count;    // tiles in this pass
+    uint32_t chunk_tiles;   // tiles per work unit (L2 reuse window)
+    int mode;
+    const float* theta;     // [nq] emission thresholds (EMIT)
+    unsigned int* cand_count;  // [nq]
+    uint32_t* cand_rows;    // [nq, cand_cap]
+    uint32_t cand_cap;
+    float* tilemax;         // [nq, tile_count * 8]: one maximum per 32-row group (TILEMAX)
+};
+
+// ---- PTX: TMA tensor load, tcgen05 ------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory written by TMA with CU_TENSOR_MAP_SWIZZLE_128B:
+// rows of 128 bytes, 8-row groups 1024 bytes apart.  Descriptor fields (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14), LBO>>4 [16,30) (unused for swizzled K-major, set to 1), SBO>>4 [32,46) = 1024>>4,
+// version=1 [46,48), layout SWIZZLE_128B = 2 [61,64).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D=F32 (1<<4), A=BF16 (1<<7), B=BF16 (1<<10), both K-major,
+// N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(G3_THREADS, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
+                 const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G3_STAGES * G3_STAGE_BYTES);
+    // bars[0..S): full, [S..2S): empty, [2S..2S+2): tmem_full, [2S+2..2S+4): tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G3_STAGES + 4);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (G3_STAGES + s); };
+    auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * G3_STAGES + b); };
+    auto tempty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * G3_STAGES + 2 + b); };
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_db);
+        for (uint32_t s = 0; s < G3_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (uint32_t b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 4);  // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tc_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const uint32_t chunks = (p.tile_count + p.chunk_tiles - 1) / p.chunk_tiles;
+    const uint32_t units = chunks * p.m_tiles;  // unit u -> (chunk = u / m_tiles, m tile = u % m_tiles):
+                                                // CTAs running together share a chunk of rows in L2
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+                const uint32_t chunk = u / p.m_tiles, mt = u - chunk * p.m_tiles;
+                const uint32_t t0 = chunk * p.chunk_tiles;
+                const uint32_t t1 = min(t0 + p.chunk_tiles, p.tile_count);
+                for (uint32_t t = t0; t < t1; ++t) {
+                    const uint32_t ntile = p.tile_first + t * p.tile_stride;
+                    for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_arrive_expect_tx(full_bar(stage), G3_STAGE_BYTES);
+                        const uint32_t a_dst = smem_base + stage * G3_STAGE_BYTES;
+                        tma_load_2d(a_dst, &tm_q, (int)(kb * G3_BLOCK_K), (int)(mt * G3_BLOCK_M), full_bar(stage));
+                        tma_load_2d(a_dst + G3_A_BYTES, &tm_db, (int)(kb * G3_BLOCK_K), (int)(ntile * G3_BLOCK_N), full_bar(stage));
+                        if (++stage == G3_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = umma_idesc_bf16(G3_BLOCK_M, G3_BLOCK_N);
+        uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0;
+        for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+            const uint32_t chunk = u / p.m_tiles;
+            const uint32_t t0 = chunk * p.chunk_tiles;
+            const uint32_t t1 = min(t0 + p.chunk_tiles, p.tile_count);
+            for (uint32_t t = t0; t < t1; ++t) {
+                mbar_wait(tempty_bar(abuf), aphase ^ 1u);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + abuf * G3_BLOCK_N;
+                for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_base + stage * G3_STAGE_BYTES;
+                        const uint64_t adesc = umma_desc_k_sw128(a_addr);
+                        const uint64_t bdesc = umma_desc_k_sw128(a_addr + G3_A_BYTES);
+#pragma unroll
+                        for (uint32_t k = 0; k < G3_BLOCK_K / G3_UMMA_K; ++k) {
+                            // advance 32 bytes (16 bf16) inside the swizzle atom: +2 in the >>4 encoded address
+                            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        tc_commit(empty_bar(stage));  // smem slot free once these MMAs retire
+                        if (kb + 1 == p.k_blocks) tc_commit(tfull_bar(abuf));  // accumulator complete
+                    }
+                    __syncwarp();
+                    if (++stage == G3_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (++abuf == 2) {
+                    abuf = 0;
+                    aphase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: one query per thread =====
+        const uint32_t quarter = (uint32_t)warp & 3u;  // TMEM lanes this warp may read
+        uint32_t abuf = 0, aphase = 0;
+        for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+            const uint32_t chunk = u / p.m_tiles, mt = u - chunk * p.m_tiles;
+            const uint32_t t0 = chunk * p.chunk_tiles;
+            const uint32_t t1 = min(t0 + p.chunk_tiles, p.tile_count);
+            const uint32_t qidx = mt * G3_BLOCK_M + quarter * 32u + (uint32_t)lane;
+            const bool qlive = qidx < p.nq;
+            float theta = INFINITY;
+            if (p.mode == G3_MODE_EMIT && qlive) theta = p.theta[qidx];
+            for (uint32_t t = t0; t < t1; ++t) {
+                const uint32_t ntile = p.tile_first + t * p.tile_stride;
+                const uint64_t row0 = (uint64_t)ntile * G3_BLOCK_N;
+                const uint32_t live_cols = (uint32_t)(p.n - row0 < G3_BLOCK_N ? p.n - row0 : G3_BLOCK_N);
+                mbar_wait(tfull_bar(abuf), aphase);
+                tc_fence_after();
+                const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + abuf * G3_BLOCK_N;
+                float gmax[G3_BLOCK_N / 32];
+#pragma unroll
+                for (uint32_t c0 = 0; c0 < G3_BLOCK_N; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld_32x32b_x32(taddr0 + c0, v);
+                    tc_wait_ld();
+                    gmax[c0 / 32] = -INFINITY;
+                    if (c0 >= live_cols) continue;  // rows past the end of the database (zero filled by TMA)
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float s = __uint_as_float(v[j]);
+                        if (c0 + j >= live_cols) s = -INFINITY;
+                        m = fmaxf(m, s);
+                    }
+                    gmax[c0 / 32] = m;
+                    if (p.mode == G3_MODE_EMIT && m > theta) {
+#pragma unroll 1
+                        for (int j = 0; j < 32; ++j) {
+                            float s = __uint_as_float(v[j]);
+                            if (s > theta && c0 + j < live_cols) {
+                                unsigned pos = atomicAdd(p.cand_count + qidx, 1u);
+                                if (pos < p.cand_cap) p.cand_rows[(size_t)qidx * p.cand_cap + pos] = (uint32_t)(row0 + c0 + j);
+                            }
+                        }
+                    }
+                }
+                if (p.mode == G3_MODE_TILEMAX && qlive) {
+                    float4* dst = reinterpret_cast<float4*>(p.tilemax + ((size_t)qidx * p.tile_count + t) * 8);
+                    dst[0] = make_float4(gmax[0], gmax[1], gmax[2], gmax[3]);
+                    dst[1] = make_float4(gmax[4], gmax[5], gmax[6], gmax[7]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(abuf));
+                if (++abuf == 2) {
+                    abuf = 0;
+                    aphase ^= 1u;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tc_dealloc(tmem_base, 512);
+    }
+}
+
+// ---- shadow copies --------------------------------------------------------------------------------
+// fp32 rows (pitch bytes) -> bf16 K-major rows of kpad elements (zero padded) + fp32 squared norms
+// + a running maximum of the row norm (for the certificate's error bound).
+__global__ void __launch_bounds__(256)
+shadow_rows_kernel(const uint8_t* __restrict__ rows, uint64_t pitch, int store, uint64_t n, int d, int kpad,
+                   __nv_bfloat16* __restrict__ out, float* __restrict__ norm2, unsigned int* __restrict__ max_norm2_bits) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t warps_total = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    float wmax = 0.0f;
+    for (uint64_t r = warp_global; r < n; r += warps_total) {
+        const uint8_t* src = rows + r * pitch;
+        __nv_bfloat16* dst = out + r * (uint64_t)kpad;
+        float acc = 0.0f;
+        for (int c = lane; c < kpad; c += 32) {
+            float v = 0.0f;
+            if (c < d) v = store == 0 ? reinterpret_cast<const float*>(src)[c] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[c]);
+            acc = fmaf(v, v, acc);
+            dst[c] = __float2bfloat16_rn(v);
+        }
+        acc = warp_sum_xor(acc);
+        if (lane == 0 && norm2) norm2[r] = acc;
+        wmax = fmaxf(wmax, acc);
+    }
+    if (lane == 0 && max_norm2_bits) atomicMax(max_norm2_bits, __float_as_uint(wmax));  // non-negative floats order as uints
+}
+
+// ---- threshold selection: theta[q] = rank-th largest of tilemax[q, 0..T) ------------------------------
+__global__ void __launch_bounds__(256)
+select_theta_kernel(const float* __restrict__ tilemax, uint32_t T, uint32_t rank, float* __restrict__ theta) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    float* a = reinterpret_cast<float*>(sm);
+    uint32_t m = 2;
+    while (m < T) m <<= 1;
+    const float* src = tilemax + (size_t)blockIdx.x * T;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) a[i] = i < T ? src[i] : -INFINITY;
+    for (uint32_t size = 2; size <= m; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+                uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                float x = a[lo], y = a[hi];
+                if (desc ? (x < y) : (x > y)) {
+                    a[lo] = y;
+                    a[hi] = x;
+                }
+            }
+        }
+    __syncthreads();
+    if (threadIdx.x == 0) theta[blockIdx.x] = a[rank < T ? rank : T - 1];
+}
+
+// ---- exact re-rank + certificate -------------------------------------------------------------------
+// One CTA per query.  Every candidate row is re-scored in fp32 with exactly the scan kernel's
+// arithmetic (lane l owns 16-byte chunks l, l+32, ...; fmaf in ascending element order; xor
+// butterfly), so the distances are bit-identical to what the nq < 20 path returns.
+struct RerankParams {
+    const uint8_t* rows;
+    uint64_t pitch_bytes;
+    uint32_t nvec;
+    int store;             // 0 fp32 rows, 1 bf16 rows
+    int d;
+    int qstride;           // floats per staged query (multiple of 8)
+    const float* q;        // [nq, d] fp32 queries (the originals, not the bf16 shadow)
+    const uint32_t* cand_rows;
+    const unsigned int* cand_count;
+    uint32_t cand_cap;
+    const float* theta;    // [nq]
+    const float* qnorm2;   // [nq]
+    const unsigned int* max_norm2_bits;
+    float eps_rel;         // proven relative bound on |approx - exact| / (|q| |y|)
+    uint64_t n;            // database rows
+    int k;
+    const int64_t* id_map;
+    float* D;
+    int64_t* I;
+    int* certified;        // [nq] 1 = result proven exact, 0 = must be recomputed by the exact scan
+};
+
+template <int METRIC>
+__global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const uint32_t qi = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float* qs = reinterpret_cast<float*>(sm);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(sm + (size_t)p.qstride * 4);
+    const uint32_t count = p.cand_count[qi];
+    const uint32_t c = count < p.cand_cap ? count : p.cand_cap;
+    uint32_t m = 2;
+    while (m < c) m <<= 1;
+    for (int i = threadIdx.x; i < p.qstride; i += blockDim.x) qs[i] = i < p.d ? p.q[(size_t)qi * p.d + i] : 0.0f;
+    for (uint32_t i = c + threadIdx.x; i < m; i += blockDim.x) keys[i] = 0ull;
+    __syncthreads();
+    const float4* q4 = reinterpret_cast<const float4*>(qs);
+    for (uint32_t j = warp; j < c; j += nw) {
+        const uint32_t row = p.cand_rows[(size_t)qi * p.cand_cap + j];
+        const uint8_t* rp = p.rows + (uint64_t)row * p.pitch_bytes;
+        float acc = 0.0f;
+        for (uint32_t ch = lane; ch < p.nvec; ch += 32) {
+            uint4 raw = ldg_nc_v4(rp + (size_t)ch * 16);
+            if (p.store == 0) {
+                float4 qv = q4[ch];
+                if (METRIC == 0) {
+                    acc = fmaf(__uint_as_float(raw.x), qv.x, acc);
+                    acc = fmaf(__uint_as_float(raw.y), qv.y, acc);
+                    acc = fmaf(__uint_as_float(raw.z), qv.z, acc);
+                    acc = fmaf(__uint_as_float(raw.w), qv.w, acc);
+                }
+            } else {
+                float4 qa = q4[2 * ch], qb = q4[2 * ch + 1];
+                if (METRIC == 0) {
+                    acc = fmaf(__uint_as_float(raw.x << 16), qa.x, acc);
+                    acc = fmaf(__uint_as_float(raw.x & 0xffff0000u), qa.y, acc);
+                    acc = fmaf(__uint_as_float(raw.y << 16), qa.z, acc);
+                    acc = fmaf(__uint_as_float(raw.y & 0xffff0000u), qa.w, acc);
+                    acc = fmaf(__uint_as_float(raw.z << 16), qb.x, acc);
+                    acc = fmaf(__uint_as_float(raw.z & 0xffff0000u), qb.y, acc);
+                    acc = fmaf(__uint_as_float(raw.w << 16), qb.z, acc);
+                    acc = fmaf(__uint_as_float(raw.w & 0xffff0000u), qb.w, acc);
+                }
+            }
+        }
+        acc = warp_sum_xor(acc);
+        if (lane == 0) keys[j] = b200_score_valid<METRIC>(acc) ? b200_make_key<METRIC>(acc, row) : 0ull;
+    }
+    // descending bitonic sort of the candidate keys
+    for (uint32_t size = 2; size <= m; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
+                uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint64_t x = keys[lo], y = keys[hi];
+                if (desc ? (x < y) : (x > y)) {
+                    keys[lo] = y;
+                    keys[hi] = x;
+                }
+            }
+        }
+    __syncthreads();
+    const int k = p.k;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        uint64_t key = (uint32_t)i < m ? keys[i] : 0ull;
+        if ((uint32_t)i >= c) key = 0ull;
+        float dist = (METRIC == 0) ? -FLT_MAX : FLT_MAX;
+        int64_t id = -1;
+        if (key != 0ull) {
+            dist = b200_key_score(key, METRIC);
+            uint32_t row = b200_key_row(key);
+            id = p.id_map ? p.id_map[row] : (int64_t)row;
+        }
+        p.D[(size_t)qi * k + i] = dist;
+        p.I[(size_t)qi * k + i] = id;
+    }
+    if (threadIdx.x == 0) {
+        // Certificate.  A row that was not emitted has approx <= theta, hence exact <= theta + eps.
+        // The answer is proven iff the k-th best exact score is strictly above that (strict: an
+        // equal score with a smaller row would win the tie).
+        const uint64_t want = (uint64_t)k < p.n ? (uint64_t)k : p.n;
+        bool ok = (count <= p.cand_cap) && (c >= want);
+        if (ok && want > 0) {
+            uint64_t kth = keys[want - 1];
+            if (kth == 0ull) {
+                ok = false;
+            } else {
+                float maxn = sqrtf(__uint_as_float(*p.max_norm2_bits));
+                float eps = p.eps_rel * sqrtf(p.qnorm2[qi]) * maxn;
+                float bound = p.theta[qi] + eps;
+                ok = b200_key_score(kth, METRIC) > bound;
+            }
+        }
+        p.certified[qi] = ok ? 1 : 0;
+    }
+}

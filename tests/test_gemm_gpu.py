@@ -1,0 +1,86 @@
+"""K3 (tcgen05 batched path) parity: ids and distances must be IDENTICAL to the exact scan path's
+contract — bit-exact against the oracle's device-order restatement — because every emitted
+candidate is re-scored in fp32 and uncertified queries are recomputed by the scan kernel."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def b200(gpu):
+    import c99_vectordb_b200 as m
+
+    return m
+
+
+def run_case(m, n, d, nq, k, store="f32", normalize=False, dup=False, ids=False, **opts):
+    db = oracle.synth_rows(n, d, 1234)
+    if dup:
+        db[n // 2: n // 2 + 1000] = db[:1000]  # exact ties across tiles
+    q = oracle.synth_rows(nq, d, 5678)
+    if normalize:
+        db = oracle.normalize_rows(db, oracle.ORDER_DEVICE)
+        q = oracle.normalize_rows(q, oracle.ORDER_DEVICE)
+    base = m.IndexFlat(d, 0, store=store)
+    base.set_option("gemm_min_nq", 32)
+    for name, v in opts.items():
+        base.set_option(name, v)
+    idv = None
+    if ids:
+        idv = np.arange(n, dtype=np.int64) * 2 + 7
+        w = m.IndexIDMap2(base)
+        w.add_with_ids(db, idv)
+        idx = w
+    else:
+        base.add(db)
+        idx = base
+    D, I = idx.search(q, k)
+    ref_db = oracle.round_bf16(db) if store == "bf16" else db
+    Dw, Iw = oracle.search(0, ref_db, q, k, ids=idv, order=oracle.ORDER_DEVICE, chunk=8 if store == "bf16" else 4)
+    stats = {s: base.get_option(s) for s in ("stat_gemm_used", "stat_gemm_fallbacks", "stat_gemm_cand_total",
+                                             "stat_gemm_pass1_us", "stat_gemm_pass2_us", "stat_gemm_rerank_us")}
+    np.testing.assert_array_equal(I, Iw, err_msg=str(stats))
+    np.testing.assert_array_equal(D, Dw, err_msg=str(stats))
+    return stats
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(70001, 768, 130, 10), (200_000, 768, 256, 100), (131072, 384, 64, 10),
+                                        (100_000, 100, 97, 17), (140_000, 1024, 33, 256)])
+def test_batched_ip_exact(b200, n, d, nq, k):
+    st = run_case(b200, n, d, nq, k)
+    assert st["stat_gemm_used"] == 1
+    assert st["stat_gemm_fallbacks"] <= nq // 4, st  # the certificate passes for almost every query
+
+
+def test_too_few_rows_for_k_stays_on_the_scan_path(b200):
+    st = run_case(b200, 66000, 1024, 33, 256)  # n < 512 k: the threshold statistic cannot resolve k
+    assert st["stat_gemm_used"] == 0
+
+
+def test_batched_normalized_with_ties_and_ids(b200):
+    st = run_case(b200, 150_000, 768, 200, 10, normalize=True, dup=True, ids=True)
+    assert st["stat_gemm_used"] == 1
+
+
+def test_batched_bf16_store(b200):
+    st = run_case(b200, 120_000, 1024, 96, 10, store="bf16", normalize=True)
+    assert st["stat_gemm_used"] == 1
+
+
+def test_uncertified_queries_fall_back_to_exact_scan(b200):
+    # an emission target of ~2k candidates cannot be certified against the bf16 bound: every query
+    # must be recomputed by the scan kernel and the answer must still be exact
+    st = run_case(b200, 80_000, 256, 40, 50, gemm_emit_factor=2, gemm_sample_tiles=64)
+    assert st["stat_gemm_fallbacks"] > 0, st
+    assert st["stat_gemm_used"] == 1
+
+
+def test_small_batches_do_not_use_gemm(b200):
+    db, q = oracle.synth_rows(70_000, 128, 1), oracle.synth_rows(8, 128, 2)
+    idx = b200.IndexFlat(128, 0)
+    idx.add(db)
+    idx.search(q, 5)
+    assert idx.get_option("stat_gemm_used") == 0
