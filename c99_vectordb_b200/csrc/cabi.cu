@@ -705,7 +705,7 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uin
 
 static bool gemm_eligible(b200_index* ix, int64_t nq, int64_t k) {
     return ix->opt_gemm_min_nq > 0 && nq >= ix->opt_gemm_min_nq && ix->metric == B200_METRIC_IP && k <= B200_FUSED_K_MAX &&
-           ix->ntotal >= 65536 && ix->ntotal >= 512 * k && ix->d >= 32 && k < ix->opt_fullrank_min_k;
+           ix->ntotal >= 65536 && ix->ntotal >= 1024 * k && ix->d >= 32 && k < ix->opt_fullrank_min_k;
 }
 
 static int ensure_shadow(b200_index* ix, cudaStream_t st) {

@@ -48,7 +48,7 @@ def run_case(m, n, d, nq, k, store="f32", normalize=False, dup=False, ids=False,
 
 
 @pytest.mark.parametrize("n,d,nq,k", [(70001, 768, 130, 10), (200_000, 768, 256, 100), (131072, 384, 64, 10),
-                                        (100_000, 100, 97, 17), (140_000, 1024, 33, 256)])
+                                        (100_000, 100, 97, 17), (300_000, 1024, 33, 256)])
 def test_batched_ip_exact(b200, n, d, nq, k):
     st = run_case(b200, n, d, nq, k)
     assert st["stat_gemm_used"] == 1
@@ -56,7 +56,7 @@ def test_batched_ip_exact(b200, n, d, nq, k):
 
 
 def test_too_few_rows_for_k_stays_on_the_scan_path(b200):
-    st = run_case(b200, 66000, 1024, 33, 256)  # n < 512 k: the threshold statistic cannot resolve k
+    st = run_case(b200, 66000, 1024, 33, 256)  # n < 1024 k: the threshold statistic cannot resolve k
     assert st["stat_gemm_used"] == 0
 
 
