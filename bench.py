@@ -337,6 +337,12 @@ def main_b200(a):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        try:
+            tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text()).get(a.workload)
+            if tr and world == 1:
+                line["roofline"]["traffic"] = tr
+        except Exception:
+            pass
         if gemm_used:
             # batched path: the dominant kernel is the tcgen05 emit pass; algorithmic flops = 2 nq N d
             p2_ms = base.get_option("stat_gemm_pass2_us") / 1e3

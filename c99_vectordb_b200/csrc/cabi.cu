@@ -77,7 +77,7 @@ struct b200_index {
     // options
     int64_t opt_variant = B200_SCAN_AUTO, opt_warps = 8, opt_stages = 0, opt_tile_rows = 0,
             opt_ctas_per_sm = 0, opt_evict_first = 0, opt_fullrank_min_k = B200_FUSED_K_MAX + 1,
-            opt_normalize_queries = 0, opt_qb = 0, opt_dynamic = 1, opt_claim_chunk = 0, opt_fused_tail = -1;
+            opt_normalize_queries = 0, opt_qb = 0, opt_dynamic = -1, opt_claim_chunk = 0, opt_fused_tail = -1;
     int64_t opt_gemm_min_nq = 64, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 64, opt_gemm_sample_tiles = 1024;
     // read-only statistics of the last batched (K3) search
     int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
@@ -490,11 +490,10 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
     const int kk = fullrank ? 1 : k;
     const size_t budget = ix->smem_optin - 1024;
     int variant = (int)ix->opt_variant;
-    // AUTO (measured, profiles/r1_sweeps.md): the TMA-staged ring wins for fp32 rows of >= 3 KB
-    // (10M x 768: 7.39 TB/s vs 6.85); short rows and bf16 rows carry more instructions per byte and
-    // want the 32 resident warps/SM of the direct-load variant (d=384: 6.63 vs 6.05 TB/s).
-    if (variant == B200_SCAN_AUTO)
-        variant = (ix->store == B200_STORE_F32 && ix->pitch >= 3072) ? B200_VARIANT_BULK : B200_VARIANT_LDG;
+    // AUTO (measured, profiles/README.md): fp32 rows -> the TMA-staged ring with dynamic tiles
+    // (10M x 768: 7.48 TB/s, 40M x 384: 7.41 TB/s); bf16 rows carry 2.5x the instructions per byte and
+    // want the 32 resident warps/SM of the direct-load variant with static tiles (6.42 vs 5.37 TB/s).
+    if (variant == B200_SCAN_AUTO) variant = (ix->store == B200_STORE_F32) ? B200_VARIANT_BULK : B200_VARIANT_LDG;
     if (variant == B200_VARIANT_BULK) {
         int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_MAX / 32);
         bool ok = false;
@@ -584,7 +583,7 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     p.nqb = nqb;
     p.k = score_keys ? 1 : k;
     p.ticket = ix->ticket;
-    p.dynamic = ix->opt_dynamic ? 1 : 0;
+    p.dynamic = ix->opt_dynamic < 0 ? (pl.variant == B200_VARIANT_BULK ? 1 : 0) : (ix->opt_dynamic ? 1 : 0);
     {
         // one atomic claim hands out a run of tiles; keep >= ~16 claims per warp for balance
         uint64_t tiles = ((uint64_t)ix->ntotal + pl.tile_rows - 1) / pl.tile_rows;

@@ -110,10 +110,14 @@ __device__ __forceinline__ void warp_list_insert(uint64_t* list, int k, int lane
 }
 
 // In-place descending bitonic sort of m (power of two) keys in shared memory by the whole CTA.
+// Pair t of a compare-exchange stage is handled by thread t % blockDim, so for strides <= 32 every
+// aligned 64-key block is touched by exactly one warp: those stages only need __syncwarp(); a block
+// barrier is needed only around stages with stride >= 64 (15 instead of 66 barriers for m = 2048).
 __device__ __forceinline__ void cta_bitonic_sort_desc(uint64_t* a, uint32_t m) {
+    __syncthreads();
     for (uint32_t size = 2; size <= m; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncthreads();
+            if (stride >= 64) __syncthreads(); else __syncwarp();
             for (uint32_t t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
                 uint32_t lo = 2 * t - (t & (stride - 1));  // index with bit `stride` clear
                 uint32_t hi = lo + stride;
@@ -125,6 +129,7 @@ __device__ __forceinline__ void cta_bitonic_sort_desc(uint64_t* a, uint32_t m) {
                     a[hi] = x;
                 }
             }
+            if (stride == 64) __syncthreads();  // the warp-local stages that follow read other warps' writes
         }
     }
     __syncthreads();
@@ -393,6 +398,34 @@ scan_topk_kernel(const ScanParams p) {
                         for (int r = 0; r < RB; ++r) acc_bf16x8<METRIC>(acc[qi][r], raw[r], qa, qb);
                     }
                 }
+            }
+            if (QB == 1 && RB == 4 && !fullrank) {
+                // Transposing butterfly: after the xor-16 and xor-8 rounds each lane carries ONE row's
+                // partial sum (row = (lane >> 3) & 3), then xor 4/2/1 finish it.  The additions are
+                // the same pairs as four separate butterflies, so scores stay bit-identical; 6 shuffles
+                // instead of 20, and one ballot decides whether any row beats the threshold.
+                const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+                float k0 = up16 ? acc[0][2] : acc[0][0], k1 = up16 ? acc[0][3] : acc[0][1];
+                float s0 = up16 ? acc[0][0] : acc[0][2], s1 = up16 ? acc[0][1] : acc[0][3];
+                k0 += __shfl_xor_sync(B200_FULL_MASK, s0, 16);
+                k1 += __shfl_xor_sync(B200_FULL_MASK, s1, 16);
+                float kk = up8 ? k1 : k0, ss = up8 ? k0 : k1;
+                kk += __shfl_xor_sync(B200_FULL_MASK, ss, 8);
+                kk += __shfl_xor_sync(B200_FULL_MASK, kk, 4);
+                kk += __shfl_xor_sync(B200_FULL_MASK, kk, 2);
+                kk += __shfl_xor_sync(B200_FULL_MASK, kk, 1);
+                const uint32_t myr = ((uint32_t)lane >> 3) & 3u;
+                const uint64_t myrow = tile_row0 + g + myr;
+                const bool live = (g + myr < rows_in_tile) && b200_score_valid<METRIC>(kk);
+                const uint64_t mykey = b200_make_key<METRIC>(kk, (uint32_t)myrow);
+                unsigned hits = __ballot_sync(B200_FULL_MASK, live && mykey > tau[0]);
+                while (hits) {  // rare: a row beats the warp's current k-th best
+                    const int src = __ffs(hits) - 1;
+                    const uint64_t key = __shfl_sync(B200_FULL_MASK, mykey, src);
+                    hits &= ~(0xFFu << (src & ~7));  // the 8 lanes of that row carry the same key
+                    if (key > tau[0]) warp_list_insert(my_lists, k, lane, key, tau[0], tau_pos[0]);
+                }
+                continue;
             }
 #pragma unroll
             for (int qi = 0; qi < QB; ++qi)

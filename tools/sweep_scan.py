@@ -72,7 +72,7 @@ def main():
         configs.append(dict(scan_variant=2, scan_dynamic_tiles=1, scan_claim_chunk=4))
         configs.append(dict(scan_variant=2, scan_dynamic_tiles=1, scan_claim_chunk=64))
     defaults = dict(scan_variant=0, scan_warps=8, scan_tile_rows=0, scan_stages=0, scan_l2_evict_first=0, scan_ctas_per_sm=0,
-                    scan_dynamic_tiles=1, scan_claim_chunk=0)
+                    scan_dynamic_tiles=-1, scan_claim_chunk=0)
     ref_I = None
     results = {i: [] for i in range(len(configs))}
     for rnd in range(a.rounds):  # interleaved rounds: drift over the call hits every configuration alike
