@@ -78,7 +78,7 @@ struct b200_index {
     int64_t opt_variant = B200_SCAN_AUTO, opt_warps = 8, opt_stages = 0, opt_tile_rows = 0,
             opt_ctas_per_sm = 0, opt_evict_first = 0, opt_fullrank_min_k = B200_FUSED_K_MAX + 1,
             opt_normalize_queries = 0, opt_qb = 0, opt_dynamic = -1, opt_claim_chunk = 0, opt_fused_tail = -1;
-    int64_t opt_gemm_min_nq = 64, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 64, opt_gemm_sample_tiles = 1024;
+    int64_t opt_gemm_min_nq = 64, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2;
     // read-only statistics of the last batched (K3) search
     int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
             stat_gemm_pass2_us = 0, stat_gemm_rerank_us = 0;
@@ -264,6 +264,7 @@ static const OptName kOpts[] = {
     {"gemm_emit_factor", &b200_index::opt_gemm_emit_factor},
     {"gemm_chunk_tiles", &b200_index::opt_gemm_chunk_tiles},
     {"gemm_sample_tiles", &b200_index::opt_gemm_sample_tiles},
+    {"gemm_cta_group", &b200_index::opt_gemm_cta_group},
     {"stat_gemm_used", &b200_index::stat_gemm_used},
     {"stat_gemm_fallbacks", &b200_index::stat_gemm_fallbacks},
     {"stat_gemm_cand_total", &b200_index::stat_gemm_cand_total},
@@ -585,10 +586,12 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     p.ticket = ix->ticket;
     p.dynamic = ix->opt_dynamic < 0 ? (pl.variant == B200_VARIANT_BULK ? 1 : 0) : (ix->opt_dynamic ? 1 : 0);
     {
-        // one atomic claim hands out a run of tiles; keep >= ~16 claims per warp for balance
+        // One atomic claim hands out a run of tiles.  The run bounds the tail (a warp finishes at
+        // most one run after the database is exhausted: run x ~2 us) while a single hot counter
+        // sustains only ~400 claims/us; >= 64 claims per warp, runs of 4..16 tiles.
         uint64_t tiles = ((uint64_t)ix->ntotal + pl.tile_rows - 1) / pl.tile_rows;
-        uint64_t per = tiles / ((uint64_t)pl.grid * pl.nw * 16);
-        p.claim_chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(per, 1), 16);
+        uint64_t per = tiles / ((uint64_t)pl.grid * pl.nw * 64);
+        p.claim_chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(per, 4), 16);
         if (ix->opt_claim_chunk > 0) p.claim_chunk = (uint32_t)ix->opt_claim_chunk;
     }
     p.fused_tail = (nqb == 1 || score_keys) ? 1 : 0;
@@ -747,9 +750,10 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     const uint32_t NT = (uint32_t)((n + G3_BLOCK_N - 1) / G3_BLOCK_N);
     const uint32_t m_tiles = (uint32_t)((nq + G3_BLOCK_M - 1) / G3_BLOCK_M);
     const uint32_t cap = 4096;
+    const int cg = ix->opt_gemm_cta_group == 1 ? 1 : 2;
     CKI(ensure_shadow(ix, st));
     // ---- scratch ----
-    const size_t qb_elems = (size_t)m_tiles * G3_BLOCK_M * kpad;
+    const size_t qb_elems = (size_t)((m_tiles + 1) / 2 * 2) * G3_BLOCK_M * kpad;  // whole 256-query groups
     // sampled tiles: each contributes 8 group maxima; at most 8192 maxima per query are sorted
     const uint32_t T = (uint32_t)std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(ix->opt_gemm_sample_tiles, 64), 1024), NT);
     const uint32_t stride = std::max<uint32_t>(1, NT / T);
@@ -776,9 +780,33 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     ++ix->launches;
     CK(cudaGetLastError());
     CUtensorMap tm_q, tm_db;
-    CKI(make_tmap_bf16(&tm_q, ix->g_qb, (uint64_t)m_tiles * G3_BLOCK_M, (uint32_t)kpad, G3_BLOCK_M));
-    CKI(make_tmap_bf16(&tm_db, ix->sh_rows, n, (uint32_t)kpad, G3_BLOCK_N));
-    CK(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G3_SMEM_BYTES));
+    CKI(make_tmap_bf16(&tm_q, ix->g_qb, (uint64_t)((m_tiles + 1) / 2 * 2) * G3_BLOCK_M, (uint32_t)kpad, G3_BLOCK_M));
+    CKI(make_tmap_bf16(&tm_db, ix->sh_rows, n, (uint32_t)kpad, G3_BLOCK_N / cg));
+    CK(cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3Cfg<1>::kSmemBytes));
+    CK(cudaFuncSetAttribute(gemm_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3Cfg<2>::kSmemBytes));
+    auto launch_gemm = [&](const GemmParams& g) -> int {
+        if (cg == 1) {
+            gemm_topk_kernel<1><<<ix->num_sms, G3_THREADS, G3Cfg<1>::kSmemBytes, st>>>(tm_q, tm_db, g);
+        } else {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3((unsigned)(ix->num_sms / 2 * 2));
+            cfg.blockDim = dim3(G3_THREADS);
+            cfg.dynamicSmemBytes = G3Cfg<2>::kSmemBytes;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<2>, tm_q, tm_db, g));
+        }
+        ++ix->launches;
+        CK(cudaGetLastError());
+        return 0;
+    };
     cudaEvent_t ev[4];
     for (auto& e : ev) CK(cudaEventCreate(&e));
     GemmParams gp;
@@ -787,7 +815,17 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     gp.m_tiles = m_tiles;
     gp.n = n;
     gp.k_blocks = (uint32_t)(kpad / G3_BLOCK_K);
-    gp.chunk_tiles = (uint32_t)std::max<int64_t>(1, ix->opt_gemm_chunk_tiles);
+    {
+        // Work units that run together share a chunk of row tiles through L2: keep the concurrently
+        // streamed chunks within ~48 MB of the 126 MB L2.
+        const uint32_t groups = (uint32_t)(ix->num_sms / cg);
+        const uint32_t m_groups = (m_tiles + cg - 1) / cg;
+        const uint32_t concurrent = (groups + m_groups - 1) / m_groups + 1;
+        const double tile_bytes = (double)G3_BLOCK_N * kpad * 2;
+        double ct = 48e6 / (concurrent * tile_bytes);
+        gp.chunk_tiles = (uint32_t)std::min(64.0, std::max(4.0, ct));
+        if (ix->opt_gemm_chunk_tiles > 0) gp.chunk_tiles = (uint32_t)ix->opt_gemm_chunk_tiles;
+    }
     gp.theta = ix->g_theta;
     gp.cand_count = ix->g_count;
     gp.cand_rows = ix->g_cand;
@@ -799,9 +837,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     gp.tile_stride = stride;
     gp.tile_count = T;
     CK(cudaEventRecord(ev[0], st));
-    gemm_topk_kernel<<<ix->num_sms, G3_THREADS, G3_SMEM_BYTES, st>>>(tm_q, tm_db, gp);
-    ++ix->launches;
-    CK(cudaGetLastError());
+    CKI(launch_gemm(gp));
     {
         // expected emissions per query = emit_factor * k.  The rank-th largest of the sampled
         // 32-row group maxima estimates the score quantile (sample rows / n) * that count; the rank
@@ -823,9 +859,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     gp.tile_stride = 1;
     gp.tile_count = NT;
     CK(cudaEventRecord(ev[1], st));
-    gemm_topk_kernel<<<ix->num_sms, G3_THREADS, G3_SMEM_BYTES, st>>>(tm_q, tm_db, gp);
-    ++ix->launches;
-    CK(cudaGetLastError());
+    CKI(launch_gemm(gp));
     CK(cudaEventRecord(ev[2], st));
     // ---- exact re-rank + certificate ----
     RerankParams rp;

@@ -118,65 +118,165 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// ---- 2-CTA helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; completion bytes are credited to the mbarrier of the
+// pair's leader (mbar is a shared::cluster address inside the leader CTA)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst_smem), "l"(map), "r"(mbar), "r"(c0), "r"(c1)
+        : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tc_alloc_cg(uint32_t smem_dst, uint32_t ncols) {
+    if (CG == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tc_dealloc_cg(uint32_t taddr, uint32_t ncols) {
+    if (CG == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tc_mma_f16_cg(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (CG == 1) {
+        tc_mma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+// arrive on `bar` when all prior MMAs retire; CG == 2: on the same barrier in both CTAs of the pair
+template <int CG>
+__device__ __forceinline__ void tc_commit_cg(uint32_t bar) {
+    if (CG == 1) {
+        tc_commit(bar);
+    } else {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"((uint16_t)3)
+                     : "memory");
+    }
+}
+
+template <int CG>
+struct G3Cfg {
+    static constexpr uint32_t kBRows = G3_BLOCK_N / CG;            // rows of the N tile staged by one CTA
+    static constexpr uint32_t kBBytes = kBRows * G3_BLOCK_K * 2;
+    static constexpr uint32_t kStageBytes = G3_A_BYTES + kBBytes;  // 48 KB (CG=1) / 32 KB (CG=2)
+    static constexpr uint32_t kStages = CG == 1 ? 4 : 6;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+// CG = 1: one CTA per 128 x 256 tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2) per
+// 256 x 256 tile — each CTA stages its own 128 queries and HALF of the 256 rows, the pair's tensor
+// cores share the row operand, which halves shared-memory traffic per SM (the cta_group::1 form is
+// capped near 2/3 of peak by the 128 B/cycle smem port: 96 B/cycle of operand reads + 96 B/cycle of
+// TMA fills).  Only the pair's leader (rank 0) issues MMAs; both CTAs run TMA and the epilogue.
+template <int CG>
 __global__ void __launch_bounds__(G3_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
                  const GemmParams p) {
+    using Cfg = G3Cfg<CG>;
     extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment for the swizzle atoms
+    // 1024-byte alignment for the swizzle atoms (identical offset in both CTAs of a pair)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G3_STAGES * G3_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
     // bars[0..S): full, [S..2S): empty, [2S..2S+2): tmem_full, [2S+2..2S+4): tmem_empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G3_STAGES + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::kStages + 4);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (G3_STAGES + s); };
-    auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * G3_STAGES + b); };
-    auto tempty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * G3_STAGES + 2 + b); };
+    auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (Cfg::kStages + s); };
+    auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * Cfg::kStages + b); };
+    auto tempty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * Cfg::kStages + 2 + b); };
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t group_id = blockIdx.x / CG, groups = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_q);
         tma_prefetch_desc(&tm_db);
-        for (uint32_t s = 0; s < G3_STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+        for (uint32_t s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(full_bar(s), 1);   // the leader's arrive.expect_tx (bytes of both CTAs land here)
+            mbar_init(empty_bar(s), 1);  // one (multicast) tcgen05.commit
         }
         for (uint32_t b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), 4);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(b), 4 * CG);  // one arrive per epilogue warp of every CTA in the pair
         }
         mbar_fence_init();
     }
-    if (warp == 1) tc_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 1) tc_alloc_cg<CG>(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const uint32_t chunks = (p.tile_count + p.chunk_tiles - 1) / p.chunk_tiles;
-    const uint32_t units = chunks * p.m_tiles;  // unit u -> (chunk = u / m_tiles, m tile = u % m_tiles):
-                                                // CTAs running together share a chunk of rows in L2
+    const uint32_t m_groups = (p.m_tiles + CG - 1) / CG;  // 128*CG queries per work unit
+    const uint32_t units = chunks * m_groups;  // unit u -> (chunk = u / m_groups, m group = u % m_groups):
+                                               // CTAs running together share a chunk of rows in L2
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (every CTA) =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-                const uint32_t chunk = u / p.m_tiles, mt = u - chunk * p.m_tiles;
+            // CG == 2: completion bytes are credited to the LEADER's full barrier
+            for (uint32_t u = group_id; u < units; u += groups) {
+                const uint32_t chunk = u / m_groups, mg = u - chunk * m_groups;
+                const uint32_t mt = mg * CG + rank;
                 const uint32_t t0 = chunk * p.chunk_tiles;
                 const uint32_t t1 = min(t0 + p.chunk_tiles, p.tile_count);
                 for (uint32_t t = t0; t < t1; ++t) {
                     const uint32_t ntile = p.tile_first + t * p.tile_stride;
                     for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
-                        mbar_arrive_expect_tx(full_bar(stage), G3_STAGE_BYTES);
-                        const uint32_t a_dst = smem_base + stage * G3_STAGE_BYTES;
-                        tma_load_2d(a_dst, &tm_q, (int)(kb * G3_BLOCK_K), (int)(mt * G3_BLOCK_M), full_bar(stage));
-                        tma_load_2d(a_dst + G3_A_BYTES, &tm_db, (int)(kb * G3_BLOCK_K), (int)(ntile * G3_BLOCK_N), full_bar(stage));
-                        if (++stage == G3_STAGES) {
+                        const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+                        const int kc = (int)(kb * G3_BLOCK_K);
+                        if (CG == 1) {
+                            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                            tma_load_2d(a_dst, &tm_q, kc, (int)(mt * G3_BLOCK_M), full_bar(stage));
+                            tma_load_2d(a_dst + G3_A_BYTES, &tm_db, kc, (int)(ntile * G3_BLOCK_N), full_bar(stage));
+                        } else {
+                            if (leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes * 2);
+                            const uint32_t lead_bar = mapa_shared(full_bar(stage), 0);
+                            tma_load_2d_cg2(a_dst, &tm_q, kc, (int)(mt * G3_BLOCK_M), lead_bar);
+                            tma_load_2d_cg2(a_dst + G3_A_BYTES, &tm_db, kc, (int)(ntile * G3_BLOCK_N + rank * Cfg::kBRows), lead_bar);
+                        }
+                        if (++stage == Cfg::kStages) {
                             stage = 0;
                             phase ^= 1u;
                         }
@@ -185,50 +285,54 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        const uint32_t idesc = umma_idesc_bf16(G3_BLOCK_M, G3_BLOCK_N);
-        uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0;
-        for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-            const uint32_t chunk = u / p.m_tiles;
-            const uint32_t t0 = chunk * p.chunk_tiles;
-            const uint32_t t1 = min(t0 + p.chunk_tiles, p.tile_count);
-            for (uint32_t t = t0; t < t1; ++t) {
-                mbar_wait(tempty_bar(abuf), aphase ^ 1u);  // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + abuf * G3_BLOCK_N;
-                for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
+        // ===== MMA issuer (the pair's leader only) =====
+        if (leader) {
+            const uint32_t idesc = umma_idesc_bf16(G3_BLOCK_M * CG, G3_BLOCK_N);
+            uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0;
+            for (uint32_t u = group_id; u < units; u += groups) {
+                const uint32_t chunk = u / m_groups;
+                const uint32_t t0 = chunk * p.chunk_tiles;
+                const uint32_t t1 = min(t0 + p.chunk_tiles, p.tile_count);
+                for (uint32_t t = t0; t < t1; ++t) {
+                    mbar_wait(tempty_bar(abuf), aphase ^ 1u);  // every epilogue warp has drained this accumulator
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t a_addr = smem_base + stage * G3_STAGE_BYTES;
-                        const uint64_t adesc = umma_desc_k_sw128(a_addr);
-                        const uint64_t bdesc = umma_desc_k_sw128(a_addr + G3_A_BYTES);
+                    const uint32_t d_tmem = tmem_base + abuf * G3_BLOCK_N;
+                    for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+                            const uint64_t adesc = umma_desc_k_sw128(a_addr);
+                            const uint64_t bdesc = umma_desc_k_sw128(a_addr + G3_A_BYTES);
 #pragma unroll
-                        for (uint32_t k = 0; k < G3_BLOCK_K / G3_UMMA_K; ++k) {
-                            // advance 32 bytes (16 bf16) inside the swizzle atom: +2 in the >>4 encoded address
-                            tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            for (uint32_t k = 0; k < G3_BLOCK_K / G3_UMMA_K; ++k) {
+                                // advance 32 bytes (16 bf16) inside the swizzle atom: +2 in the >>4 encoded address
+                                tc_mma_f16_cg<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            }
+                            tc_commit_cg<CG>(empty_bar(stage));  // smem slot free (in both CTAs) once these MMAs retire
+                            if (kb + 1 == p.k_blocks) tc_commit_cg<CG>(tfull_bar(abuf));  // accumulator complete
                         }
-                        tc_commit(empty_bar(stage));  // smem slot free once these MMAs retire
-                        if (kb + 1 == p.k_blocks) tc_commit(tfull_bar(abuf));  // accumulator complete
+                        __syncwarp();
+                        if (++stage == Cfg::kStages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
                     }
-                    __syncwarp();
-                    if (++stage == G3_STAGES) {
-                        stage = 0;
-                        phase ^= 1u;
+                    if (++abuf == 2) {
+                        abuf = 0;
+                        aphase ^= 1u;
                     }
-                }
-                if (++abuf == 2) {
-                    abuf = 0;
-                    aphase ^= 1u;
                 }
             }
         }
     } else {
-        // ===== epilogue: one query per thread =====
+        // ===== epilogue: one query per thread (every CTA reads its own 128 TMEM lanes) =====
         const uint32_t quarter = (uint32_t)warp & 3u;  // TMEM lanes this warp may read
+        const uint32_t tempty_lead0 = CG == 1 ? tempty_bar(0) : mapa_shared(tempty_bar(0), 0);
         uint32_t abuf = 0, aphase = 0;
-        for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-            const uint32_t chunk = u / p.m_tiles, mt = u - chunk * p.m_tiles;
+        for (uint32_t u = group_id; u < units; u += groups) {
+            const uint32_t chunk = u / m_groups, mg = u - chunk * m_groups;
+            const uint32_t mt = mg * CG + rank;
             const uint32_t t0 = chunk * p.chunk_tiles;
             const uint32_t t1 = min(t0 + p.chunk_tiles, p.tile_count);
             const uint32_t qidx = mt * G3_BLOCK_M + quarter * 32u + (uint32_t)lane;
@@ -259,13 +363,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     }
                     gmax[c0 / 32] = m;
                     if (p.mode == G3_MODE_EMIT && m > theta) {
-#pragma unroll 1
-                        for (int j = 0; j < 32; ++j) {
-                            float s = __uint_as_float(v[j]);
-                            if (s > theta && c0 + j < live_cols) {
-                                unsigned pos = atomicAdd(p.cand_count + qidx, 1u);
-                                if (pos < p.cand_cap) p.cand_rows[(size_t)qidx * p.cand_cap + pos] = (uint32_t)(row0 + c0 + j);
-                            }
+                        // rare (this thread's query has a candidate among these 32 rows): build the
+                        // hit mask in registers, then append the rows
+                        uint32_t hit = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            hit |= (__uint_as_float(v[j]) > theta && c0 + j < live_cols) ? (1u << j) : 0u;
+                        while (hit) {
+                            const int j = __ffs(hit) - 1;
+                            hit &= hit - 1;
+                            unsigned pos = atomicAdd(p.cand_count + qidx, 1u);
+                            if (pos < p.cand_cap) p.cand_rows[(size_t)qidx * p.cand_cap + pos] = (uint32_t)(row0 + c0 + j);
                         }
                     }
                 }
@@ -276,7 +384,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar(abuf));
+                if (lane == 0) {
+                    if (CG == 1) mbar_arrive(tempty_bar(abuf));
+                    else mbar_arrive_cluster(tempty_lead0 + 8u * abuf);  // the leader's MMA warp waits for both CTAs
+                }
                 if (++abuf == 2) {
                     abuf = 0;
                     aphase ^= 1u;
@@ -287,9 +398,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // nobody leaves while its pair still touches its smem / TMEM
     if (warp == 1) {
         tc_fence_after();
-        tc_dealloc(tmem_base, 512);
+        tc_dealloc_cg<CG>(tmem_base, 512);
     }
 }
 

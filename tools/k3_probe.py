@@ -9,6 +9,7 @@ from oracle import oracle
 n, d, nq, k = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 idx = m.IndexFlat(d, 0)
 idx.set_option("gemm_min_nq", 32)
+if len(sys.argv) > 5: idx.set_option("gemm_cta_group", int(sys.argv[5]))
 idx.add_synthetic(n, 1234)
 q = oracle.synth_rows(nq, d, 5678)
 t0 = time.time(); D, I = idx.search(q, k); t1 = time.time()
