@@ -35,6 +35,8 @@ SIGNATURES = [
     ("b200_index_add_synthetic", C.c_int, [_h, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int64]),
     ("b200_index_search", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     ("b200_index_search_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("b200_index_search_masked", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("b200_index_search_masked_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("b200_index_launch_count", C.c_int64, [_h]),
     ("b200_index_sync", C.c_int, [_h]),
     ("b200_index_ntotal", C.c_int64, [_h]),

@@ -96,6 +96,9 @@ struct b200_index {
     uint32_t* g_cand = nullptr;
     int* g_cert = nullptr;
     size_t g_qb_cap = 0, g_q_cap = 0, g_tilemax_cap = 0, g_cand_cap = 0;
+    const uint32_t* cur_mask = nullptr;  // row bitmap of the search in flight (device), or null
+    uint32_t* mask_dev = nullptr;        // staging for host masks
+    size_t mask_cap = 0;
     int64_t launches = 0;
 };
 
@@ -178,6 +181,7 @@ extern "C" int b200_index_destroy(b200_index* ix) {
     cudaFree(ix->fr_hi);
     for (int i = 0; i < 4; ++i) cudaFree(ix->fr_buf[i]);
     cudaFree(ix->fr_hist);
+    cudaFree(ix->mask_dev);
     cudaFree(ix->sh_rows);
     cudaFree(ix->sh_norm2);
     cudaFree(ix->sh_maxnorm);
@@ -605,6 +609,7 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     p.tile_bytes = pl.tile_bytes;
     p.evict_first = (int)ix->opt_evict_first;
     p.score_keys = score_keys;
+    p.row_mask = ix->cur_mask;
     p.scratch_keys = pl.scratch_keys;
     if (!score_keys) {
         size_t need = (size_t)pl.grid * pl.qb * k;
@@ -983,7 +988,7 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
     const bool fullrank = k >= ix->opt_fullrank_min_k || k > B200_FUSED_K_MAX;
     ix->stat_gemm_used = 0;
     if (!fullrank) {
-        if (gemm_eligible(ix, nq, k)) {
+        if (!ix->cur_mask && gemm_eligible(ix, nq, k)) {
             // K3 in blocks of at most 16384 queries (bounds the candidate scratch)
             for (int64_t q0 = 0; q0 < nq; q0 += 16384) {
                 int64_t nb = std::min<int64_t>(16384, nq - q0);
@@ -1068,6 +1073,34 @@ extern "C" int b200_index_search(b200_index* ix, const float* q_host, int64_t nq
         CK(cudaStreamSynchronize(st));
     }
     return 0;
+}
+
+
+extern "C" int b200_index_search_masked_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k,
+                                            const uint32_t* mask_dev, float* D_dev, int64_t* I_dev, void* stream) {
+    if (!ix) return fail("null index");
+    ix->cur_mask = mask_dev;
+    int rc = b200_index_search_dev(ix, q_dev, nq, k, D_dev, I_dev, stream);
+    ix->cur_mask = nullptr;
+    return rc;
+}
+
+extern "C" int b200_index_search_masked(b200_index* ix, const float* q_host, int64_t nq, int64_t k,
+                                        const uint32_t* mask_host, float* D_host, int64_t* I_host) {
+    if (!ix) return fail("null index");
+    if (!mask_host) return b200_index_search(ix, q_host, nq, k, D_host, I_host);
+    CKI(use_device(ix));
+    const size_t words = ((size_t)ix->ntotal + 31) / 32;
+    if (words == 0) return b200_index_search(ix, q_host, nq, k, D_host, I_host);
+    if (ix->mask_cap < words) {
+        CK(cudaStreamSynchronize(ix->stream));
+        CKI(grow(&ix->mask_dev, &ix->mask_cap, words));
+    }
+    CK(cudaMemcpyAsync(ix->mask_dev, mask_host, words * 4, cudaMemcpyHostToDevice, ix->stream));
+    ix->cur_mask = ix->mask_dev;
+    int rc = b200_index_search(ix, q_host, nq, k, D_host, I_host);
+    ix->cur_mask = nullptr;
+    return rc;
 }
 
 extern "C" int64_t b200_index_launch_count(b200_index* ix) { return ix ? ix->launches : -1; }

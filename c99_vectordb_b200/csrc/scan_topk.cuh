@@ -55,6 +55,7 @@ struct ScanParams {
     uint32_t tile_bytes;      // BULK: tile_rows * pitch_bytes
     int evict_first;          // BULK: L2 evict-first hint on the stream
     uint32_t* score_keys;     // full-rank mode: [nqb, n] hi keys, else null
+    const uint32_t* row_mask; // optional bitmap over rows (bit r of word r>>5): 0 = row excluded
     uint32_t scratch_keys;    // power of two >= max(warps*k, B200_FINAL_BUF_KEYS)
 };
 
@@ -416,7 +417,8 @@ scan_topk_kernel(const ScanParams p) {
                 kk += __shfl_xor_sync(B200_FULL_MASK, kk, 1);
                 const uint32_t myr = ((uint32_t)lane >> 3) & 3u;
                 const uint64_t myrow = tile_row0 + g + myr;
-                const bool live = (g + myr < rows_in_tile) && b200_score_valid<METRIC>(kk);
+                bool live = (g + myr < rows_in_tile) && b200_score_valid<METRIC>(kk);
+                if (p.row_mask && live) live = (__ldg(p.row_mask + (myrow >> 5)) >> (myrow & 31)) & 1u;
                 const uint64_t mykey = b200_make_key<METRIC>(kk, (uint32_t)myrow);
                 unsigned hits = __ballot_sync(B200_FULL_MASK, live && mykey > tau[0]);
                 while (hits) {  // rare: a row beats the warp's current k-th best
@@ -440,7 +442,8 @@ scan_topk_kernel(const ScanParams p) {
                     if (g + r >= rows_in_tile) break;
                     const uint64_t row = tile_row0 + g + r;
                     const float sc = acc[qi][r];
-                    const bool valid = b200_score_valid<METRIC>(sc);
+                    bool valid = b200_score_valid<METRIC>(sc);
+                    if (p.row_mask && valid) valid = (__ldg(p.row_mask + (row >> 5)) >> (row & 31)) & 1u;
                     if (fullrank) {
                         if (lane == 0)
                             p.score_keys[(size_t)qi * p.n + row] = valid ? b200_key_hi<METRIC>(sc) : 0u;

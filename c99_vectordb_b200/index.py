@@ -63,6 +63,16 @@ def vector_to_array(v) -> np.ndarray:
     return np.array(v, copy=True)
 
 
+def pack_row_mask(row_mask, ntotal: int) -> np.ndarray:
+    """bool[ntotal] -> the uint32 bitmap include/b200_flat.h defines (bit r&31 of word r>>5)."""
+    m = np.ascontiguousarray(row_mask, dtype=bool)
+    assert m.shape == (ntotal,), "row_mask must have one entry per stored row"
+    words = (ntotal + 31) // 32
+    padded = np.zeros(words * 32, dtype=bool)
+    padded[:ntotal] = m
+    return np.packbits(padded, bitorder="little").view("<u4").copy()
+
+
 class Index:
     """Common base (faiss.Index)."""
 
@@ -159,14 +169,21 @@ class IndexFlat(Index):
         _cabi.check(_cabi.load().b200_index_add_synthetic(self._h, int(n), int(seed), int(first_row),
                                                           int(self.normalize), int(with_ids), int(first_id)))
 
-    def search(self, x, k: int):
+    def search(self, x, k: int, row_mask=None):
+        """faiss Index.search.  `row_mask` (extension, SURVEY.md 8f-1): bool array over row positions;
+        only rows whose entry is True can be returned — the filter runs inside the scan kernel."""
         x = self._coerce_x(x)
         k = int(k)
         assert k > 0
         nq = x.shape[0]
         D = np.empty((nq, k), dtype=np.float32)
         I = np.empty((nq, k), dtype=np.int64)
-        _cabi.check(_cabi.load().b200_index_search(self._h, x.ctypes.data, nq, k, D.ctypes.data, I.ctypes.data))
+        if row_mask is None:
+            _cabi.check(_cabi.load().b200_index_search(self._h, x.ctypes.data, nq, k, D.ctypes.data, I.ctypes.data))
+        else:
+            bits = pack_row_mask(row_mask, self.ntotal)
+            _cabi.check(_cabi.load().b200_index_search_masked(self._h, x.ctypes.data, nq, k, bits.ctypes.data,
+                                                              D.ctypes.data, I.ctypes.data))
         return D, I
 
     def search_device(self, q, k: int, D=None, I=None, stream: int | None = None):
@@ -257,8 +274,12 @@ class IndexIDMap(Index):
     def add(self, x) -> None:
         raise RuntimeError("add does not make sense with IndexIDMap, use add_with_ids")  # as faiss
 
-    def search(self, x, k: int):
-        return self.index.search(x, k)
+    def search(self, x, k: int, row_mask=None, ids_allowed=None):
+        """`ids_allowed` (extension): iterable of record ids that may be returned (filter push-down)."""
+        if ids_allowed is not None:
+            allowed = np.fromiter((int(i) for i in ids_allowed), dtype=np.int64)
+            row_mask = np.isin(self.index._ids(), allowed)
+        return self.index.search(x, k, row_mask=row_mask)
 
     def search_device(self, q, k: int, **kw):
         return self.index.search_device(q, k, **kw)

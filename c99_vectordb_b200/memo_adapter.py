@@ -127,3 +127,33 @@ def search_all(index: _ix.IndexIDMap2, query_vec: np.ndarray, k: int | None = No
     kk = int(index.ntotal) if k is None else int(k)
     scores, ids = index.search(np.asarray(query_vec, dtype=np.float32).reshape(1, -1), kk)
     return [Result(int(i), float(s)) for s, i in zip(scores[0].tolist(), ids[0].tolist()) if i >= 0]
+
+
+def search_filtered(index: _ix.IndexIDMap2, query_vec: np.ndarray, k: int, allowed_ids: Iterable[int]) -> list[Result]:
+    """Filter first, then rank (what SKILL.md:243-247 documents and memo_cli.py:479-506 does the other
+    way round): the metadata predicate is evaluated on the host, becomes a row bitmap, and the scan
+    kernel returns the best k among the allowed records only — no k = ntotal ranking, no O(N) Python
+    loop."""
+    if index.ntotal == 0:
+        return []
+    scores, ids = index.search(np.asarray(query_vec, dtype=np.float32).reshape(1, -1), int(k), ids_allowed=allowed_ids)
+    return [Result(int(i), float(s)) for s, i in zip(scores[0].tolist(), ids[0].tolist()) if i >= 0]
+
+
+def recall(index: _ix.IndexIDMap2, texts: Sequence[str | None], metas: Sequence[dict | None], query_vec: np.ndarray,
+           k: int, predicate: Callable[[dict], bool] | None = None) -> list[Result]:
+    """The selection loop of command_recall (memo_cli.py:491-521) with the filter pushed down: a record
+    is eligible iff its id indexes `texts`, its body is not blank and (when a predicate is given) it has
+    non-empty metadata that satisfies the predicate; the first k eligible results best-first, dropping
+    scores below -0.9 (:494)."""
+    eligible = []
+    for doc_id, text in enumerate(texts):
+        if is_blank_body(text or ""):
+            continue
+        if predicate is not None:
+            rec = metas[doc_id] if doc_id < len(metas) and metas[doc_id] is not None else {}
+            if not rec or not predicate(rec):
+                continue
+        eligible.append(doc_id)
+    out = search_filtered(index, query_vec, k, eligible)
+    return [r for r in out if not (r.score < -0.9)][:k]

@@ -98,6 +98,14 @@ int b200_index_search(b200_index* ix, const float* q_host, int64_t nq, int64_t k
  * (a cudaStream_t; NULL = the handle's own stream) and NOT synchronised. */
 int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev,
                           int64_t* I_dev, void* stream);
+/* filtered search (push memo's metadata filter down into the scan instead of
+ * k = ntotal + Python post-filter, memo_cli.py:291, :491-521).  mask is a bitmap over ROW
+ * POSITIONS, ceil(ntotal/32) uint32 words, bit (r & 31) of word r >> 5 set = row r may be returned;
+ * NULL = no filter.  Always served by the exact scan kernels. */
+int b200_index_search_masked(b200_index* ix, const float* q_host, int64_t nq, int64_t k,
+                             const uint32_t* mask_host, float* D_host, int64_t* I_host);
+int b200_index_search_masked_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k,
+                                 const uint32_t* mask_dev, float* D_dev, int64_t* I_dev, void* stream);
 /* kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t b200_index_launch_count(b200_index* ix);
 /* block until the handle's stream is idle */

@@ -86,3 +86,54 @@ np.savez(OUT / "adapter.npz", records=np.array([r if r is not None else "\x00NON
          queries=np.array(queries, dtype=object), qvecs=qvecs,
          res_ids=np.stack(res_ids), res_scores=np.stack(res_scores), allow_pickle=True)
 print("wrote", [p.name for p in OUT.glob("*.npz")])
+
+# ---- filtered recall: the reference's own command_recall --yaml --filter ----------
+import contextlib  # noqa: E402
+import io  # noqa: E402
+import tempfile  # noqa: E402
+
+import yaml  # noqa: E402
+
+fr_texts = [t for t in texts[:40]]
+fr_texts[5] = ""  # blank body: never shown (memo_cli.py:509)
+fr_metas = []
+for i in range(len(fr_texts)):
+    if i % 7 == 3:
+        fr_metas.append(None)  # records without metadata never match a filter (memo_cli.py:502-504)
+    else:
+        fr_metas.append({"priority": i % 5, "topic": ["gpu", "memo", "yaml"][i % 3], "tags": ["a", "b"] if i % 2 else ["c"]})
+filters = [None, "priority: {$gte: 3}", "topic: gpu", "{$or: [{topic: memo}, {priority: 0}]}", "tags: {$contains: b}", "priority: 99"]
+fr_queries = ["alpha beta gamma", "gpu kernel warp tile", "peanuts allergies", "omega psi chi"]
+with tempfile.TemporaryDirectory() as td:
+    idx_path, yaml_path = memo_cli.build_db_paths("frdb", td)
+    memo_cli.save_yaml_tables(yaml_path, fr_texts, fr_metas)
+    fr_index = memo_cli.rebuild_index_from_texts(fr_texts, verbose=False)
+    stub_faiss_oracle.write_index(fr_index, str(idx_path))
+    cases = []
+    for qtext in fr_queries:
+        for f in filters:
+            for kk in (1, 3, 10):
+                buf = io.StringIO()
+                with contextlib.redirect_stdout(buf):
+                    rc = memo_cli.command_recall("frdb", qtext, kk, f, True, td)
+                assert rc == 0
+                res = yaml.safe_load(buf.getvalue())["results"]
+                cases.append((qtext, f, kk, [r["id"] for r in res], [r["score"] for r in res]))
+fr_kept = [i for i, t in enumerate(fr_texts) if not memo_cli.is_blank_body(t or "")]
+eligible = {}
+for f in filters:
+    if f is None:
+        eligible["None"] = fr_kept
+    else:
+        fd = memo_cli.parse_yaml_flow_map(f)
+        eligible[f] = [i for i in fr_kept if fr_metas[i] and memo_cli.matches_filter(fr_metas[i], fd)]
+np.savez(OUT / "recall_filter.npz",
+         kept=np.array(fr_kept, dtype=np.int64),
+         kept_vectors=np.stack([memo_cli.embed_text_hash(fr_texts[i]) for i in fr_kept]).astype(np.float32),
+         queries=np.array(fr_queries, dtype=object),
+         qvecs=np.stack([memo_cli.embed_text_hash(q) for q in fr_queries]).astype(np.float32),
+         filters=np.array([str(f) for f in filters], dtype=object),
+         eligible=np.array([np.array(eligible[str(f)], dtype=np.int64) for f in filters], dtype=object),
+         cases=np.array([(q, str(f), kk, np.array(ids, dtype=np.int64), np.array(sc, dtype=np.float64)) for q, f, kk, ids, sc in cases], dtype=object),
+         allow_pickle=True)
+print("wrote recall_filter.npz with", len(cases), "cases")

@@ -366,3 +366,56 @@ def test_large_scan_against_fp64_truth(b200, metric, n, d, norm):
         Dw, Iw = oracle.search(metric, db, qn, 10, order=oracle.ORDER_DEVICE)
         np.testing.assert_array_equal(I, Iw)
         np.testing.assert_array_equal(D, Dw)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("variant", ["bulk", "ldg"])
+def test_masked_search_equals_search_over_the_allowed_rows(b200, metric, variant):
+    """Filter push-down: the masked top-k equals an unmasked search over the allowed rows only."""
+    n, d = 30011, 96
+    db, q = oracle.synth_rows(n, d, 21), oracle.synth_rows(5, d, 22)
+    db[100:200] = db[300:400]  # exact ties straddling the mask
+    rng = np.random.default_rng(3)
+    ids = np.arange(n, dtype=np.int64) * 2 + 1
+    idx = make_index(b200, metric, d, db, ids, variant=variant)
+    for frac in (0.5, 0.01, 0.0):
+        mask = rng.random(n) < frac
+        mask[150] = mask[350] = frac > 0
+        rows = np.nonzero(mask)[0]
+        for k in (1, 10, 300):  # fused and full-ranking paths
+            D, I = idx.search(q, k, row_mask=mask)
+            Dw, Iw = oracle.search(metric, db[rows], q, k, ids=ids[rows], order=oracle.ORDER_DEVICE)
+            np.testing.assert_array_equal(I, Iw)
+            np.testing.assert_array_equal(D, Dw)
+    D, I = idx.search(q, 5, ids_allowed=[ids[7], ids[9], 123456789])
+    assert set(I[0].tolist()) == {int(ids[7]), int(ids[9]), -1}
+
+
+def test_filtered_recall_against_reference_command_recall(b200):
+    """memo_adapter.search_filtered (filter first, masked top-k) returns what the REFERENCE's
+    command_recall --filter prints after ranking everything and post-filtering (memo_cli.py:479-521);
+    golden generated by tests/golden/make_golden.py from the unmodified memo_cli.py."""
+    from c99_vectordb_b200 import memo_adapter as ma
+
+    g = np.load(GOLDEN / "recall_filter.npz", allow_pickle=True)
+    idx = ma.create_index()
+    idx.add_with_ids(g["kept_vectors"], g["kept"])
+    qvec = {q: v for q, v in zip(g["queries"].tolist(), g["qvecs"])}
+    elig = {f: e for f, e in zip(g["filters"].tolist(), g["eligible"])}
+    for qtext, f, kk, ids_ref, sc_ref in g["cases"]:
+        res = ma.search_filtered(idx, qvec[qtext], int(kk), elig[f].tolist())
+        assert len(res) == len(ids_ref), (qtext, f, kk)
+        np.testing.assert_allclose([r.score for r in res], sc_ref, rtol=1e-5, atol=1e-6)
+        # near-tied scores may swap inside a group (ids compared as sets per group); the LAST group may be
+        # cut by k and keep a different member of the tie, so there only membership in the filter is checked
+        got = [r.doc_id for r in res]
+        start, n_res = 0, len(ids_ref)
+        for i in range(1, n_res + 1):
+            if i == n_res or abs(float(sc_ref[i]) - float(sc_ref[i - 1])) > 2e-6:
+                if i < n_res:
+                    assert sorted(got[start:i]) == sorted(ids_ref[start:i].tolist()), (qtext, f, kk, got, ids_ref)
+                else:
+                    assert set(got[start:i]) <= set(elig[f].tolist())
+                start = i
+        got_all = ma.search_filtered(idx, qvec[qtext], len(g["kept"]), elig[f].tolist())
+        assert sorted(r.doc_id for r in got_all) == sorted(elig[f].tolist())
