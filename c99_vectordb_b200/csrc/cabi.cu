@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -96,6 +97,9 @@ struct b200_index {
     uint32_t* g_cand = nullptr;
     int* g_cert = nullptr;
     size_t g_qb_cap = 0, g_q_cap = 0, g_tilemax_cap = 0, g_cand_cap = 0;
+    uint8_t* up_pin[2] = {nullptr, nullptr};  // pinned upload ring for bulk host adds
+    cudaEvent_t up_ev[2] = {nullptr, nullptr};
+    size_t up_chunk = 0;
     const uint32_t* cur_mask = nullptr;  // row bitmap of the search in flight (device), or null
     uint32_t* mask_dev = nullptr;        // staging for host masks
     size_t mask_cap = 0;
@@ -181,6 +185,10 @@ extern "C" int b200_index_destroy(b200_index* ix) {
     cudaFree(ix->fr_hi);
     for (int i = 0; i < 4; ++i) cudaFree(ix->fr_buf[i]);
     cudaFree(ix->fr_hist);
+    for (int i = 0; i < 2; ++i) {
+        if (ix->up_pin[i]) cudaFreeHost(ix->up_pin[i]);
+        if (ix->up_ev[i]) cudaEventDestroy(ix->up_ev[i]);
+    }
     cudaFree(ix->mask_dev);
     cudaFree(ix->sh_rows);
     cudaFree(ix->sh_norm2);
@@ -328,6 +336,67 @@ static int ingest_dev(int d, int d_pad, int store, const float* src_dev, uint8_t
     return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// bulk host -> device upload: pageable user memory is copied by a few host threads into a
+// double-buffered PINNED ring, each buffer then moves by one asynchronous DMA — the host copy of
+// chunk c+1 overlaps the DMA of chunk c (a plain cudaMemcpy from pageable memory measured 11 GB/s).
+// `consume(dev_ptr_of_chunk, chunk_offset_bytes, chunk_bytes)` is called after each chunk's DMA has
+// been enqueued (used to launch the K1 ingest kernel on staged chunks).
+// ---------------------------------------------------------------------------------------------
+static void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t bytes, int threads) {
+    if (threads <= 1 || bytes < ((size_t)4 << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    size_t per = (bytes + threads - 1) / threads;
+    per = (per + 4095) & ~(size_t)4095;
+    for (int t = 0; t < threads; ++t) {
+        size_t off = (size_t)t * per;
+        if (off >= bytes) break;
+        size_t len = std::min(per, bytes - off);
+        th.emplace_back([=] { memcpy(dst + off, src + off, len); });
+    }
+    for (auto& t : th) t.join();
+}
+
+template <typename Consume>
+static int upload_staged(b200_index* ix, const uint8_t* src, size_t bytes, uint8_t* dst_dev, bool dst_is_ring,
+                         size_t align, Consume consume) {
+    const size_t kChunk = (size_t)64 << 20;
+    size_t chunk = kChunk / align * align;
+    if (chunk == 0) chunk = align;
+    if (!ix->up_pin[0] || ix->up_chunk < chunk) {
+        for (int i = 0; i < 2; ++i) {
+            if (ix->up_pin[i]) CK(cudaFreeHost(ix->up_pin[i]));
+            ix->up_pin[i] = nullptr;
+            CK(cudaHostAlloc((void**)&ix->up_pin[i], chunk, cudaHostAllocDefault));
+            if (!ix->up_ev[i]) CK(cudaEventCreateWithFlags(&ix->up_ev[i], cudaEventDisableTiming));
+        }
+        ix->up_chunk = chunk;
+    }
+    unsigned hc = std::thread::hardware_concurrency();
+    int threads = (int)std::min<unsigned>(8, std::max<unsigned>(1, hc / 2));
+    cudaStream_t st = ix->stream;
+    size_t off = 0;
+    int b = 0;
+    bool used[2] = {false, false};
+    while (off < bytes) {
+        size_t len = std::min(chunk, bytes - off);
+        if (used[b]) CK(cudaEventSynchronize(ix->up_ev[b]));  // the DMA that last read this buffer is done
+        parallel_memcpy(ix->up_pin[b], src + off, len, threads);
+        uint8_t* target = dst_is_ring ? dst_dev : dst_dev + off;
+        CK(cudaMemcpyAsync(target, ix->up_pin[b], len, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ix->up_ev[b], st));
+        used[b] = true;
+        CKI(consume(target, off, len));
+        off += len;
+        b ^= 1;
+    }
+    return 0;
+}
+
 static int note_ids(b200_index* ix, bool explicit_ids) {
     int want = explicit_ids ? 1 : 2;
     if (ix->ntotal > 0 && ix->ids_state != 0 && ix->ids_state != want)
@@ -351,28 +420,38 @@ static int add_common(b200_index* ix, const float* x, bool x_is_dev, int64_t n, 
                            x_is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     uint8_t* dst = ix->rows + (size_t)ix->ntotal * ix->pitch;
     const bool plain = (ix->store == B200_STORE_F32) && !normalize && (ix->d == ix->d_pad);
-    if (plain) {
+    const size_t row_bytes = (size_t)ix->d * 4;
+    const bool big_host = !x_is_dev && (size_t)n * row_bytes >= ((size_t)8 << 20);
+    if (plain && (x_is_dev || !big_host)) {
         CK(cudaMemcpyAsync(dst, x, (size_t)n * ix->pitch,
                            x_is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    } else if (plain) {
+        // fp32 rows stored verbatim: pinned ring straight into the resident rows
+        CKI(upload_staged(ix, (const uint8_t*)x, (size_t)n * row_bytes, dst, false, row_bytes,
+                          [](uint8_t*, size_t, size_t) { return 0; }));
     } else if (x_is_dev) {
         CKI(ingest_dev(ix->d, ix->d_pad, ix->store, x, dst, ix->pitch, n, normalize, ix->num_sms, st, &ix->launches));
     } else {
-        // host rows: stage through a device buffer in chunks, K1 writes the resident rows
-        const size_t row_bytes = (size_t)ix->d * 4;
-        size_t chunk_rows = std::max<size_t>(1, ((size_t)256 << 20) / row_bytes);
-        chunk_rows = std::min<size_t>(chunk_rows, (size_t)n);
-        if (ix->stage_cap < chunk_rows * row_bytes) {
+        // host rows that need K1 (normalise / bf16 / padding): pinned ring -> device staging -> K1
+        const size_t chunk_bytes = std::max(row_bytes, (((size_t)64 << 20) / row_bytes) * row_bytes);
+        if (ix->stage_cap < chunk_bytes) {
             if (ix->stage) CK(cudaFree(ix->stage));
             ix->stage = nullptr;
             ix->stage_cap = 0;
-            CK(cudaMalloc((void**)&ix->stage, chunk_rows * row_bytes));
-            ix->stage_cap = chunk_rows * row_bytes;
+            CK(cudaMalloc((void**)&ix->stage, chunk_bytes));
+            ix->stage_cap = chunk_bytes;
         }
-        for (int64_t r0 = 0; r0 < n; r0 += (int64_t)chunk_rows) {
-            int64_t nr = std::min<int64_t>((int64_t)chunk_rows, n - r0);
-            CK(cudaMemcpyAsync(ix->stage, x + (size_t)r0 * ix->d, (size_t)nr * row_bytes, cudaMemcpyHostToDevice, st));
-            CKI(ingest_dev(ix->d, ix->d_pad, ix->store, ix->stage, dst + (size_t)r0 * ix->pitch, ix->pitch, nr,
-                           normalize, ix->num_sms, st, &ix->launches));
+        if (big_host) {
+            CKI(upload_staged(ix, (const uint8_t*)x, (size_t)n * row_bytes, (uint8_t*)ix->stage, true, row_bytes,
+                              [&](uint8_t* dev_chunk, size_t off, size_t len) {
+                                  int64_t r0 = (int64_t)(off / row_bytes), nr = (int64_t)(len / row_bytes);
+                                  return ingest_dev(ix->d, ix->d_pad, ix->store, (const float*)dev_chunk,
+                                                    dst + (size_t)r0 * ix->pitch, ix->pitch, nr, normalize, ix->num_sms, st,
+                                                    &ix->launches);
+                              }));
+        } else {
+            CK(cudaMemcpyAsync(ix->stage, x, (size_t)n * row_bytes, cudaMemcpyHostToDevice, st));
+            CKI(ingest_dev(ix->d, ix->d_pad, ix->store, ix->stage, dst, ix->pitch, n, normalize, ix->num_sms, st, &ix->launches));
         }
     }
     CK(cudaStreamSynchronize(st));

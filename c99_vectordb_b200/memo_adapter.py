@@ -47,8 +47,36 @@ def bag_of_hashed_words(text: str, dim: int = DIM, hash_fn: Callable[[str], int]
     return vec
 
 
-def embed_texts(texts: Sequence[str], dim: int = DIM, hash_fn: Callable[[str], int] = hash) -> np.ndarray:
-    """[n, dim] un-normalised rows; normalisation happens on the device at add / search time (K1)."""
+def stable_hash(token: str) -> int:
+    """CPython's hash(str) with the PYTHONHASHSEED=0 key (SipHash-1-3, zero key): the same in every
+    process, unlike the builtin the reference calls (memo_cli.py:163)."""
+    from . import _cabi
+
+    b = token.encode("utf-8")
+    return int(_cabi.load().b200_py_hash_seed0(b, len(b)))
+
+
+def embed_texts_stable(texts: Sequence[str], dim: int = DIM) -> np.ndarray:
+    """Native bulk embedder: [n, dim] un-normalised rows, bit-identical to the reference's
+    embed_text_hash buckets under PYTHONHASHSEED=0.  One C call instead of a Python token loop."""
+    from . import _cabi
+
+    low = [t.lower().encode("utf-8") for t in texts]  # str.lower() stays in Python (Unicode case rules)
+    offsets = np.zeros(len(low) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in low], out=offsets[1:])
+    blob = b"".join(low)
+    out = np.empty((len(low), dim), dtype=np.float32)
+    rc = _cabi.load().b200_hash_embed(blob, offsets.ctypes.data, len(low), dim, out.ctypes.data)
+    if rc:
+        raise RuntimeError("b200_hash_embed failed")
+    return out
+
+
+def embed_texts(texts: Sequence[str], dim: int = DIM, hash_fn: Callable[[str], int] | None = hash) -> np.ndarray:
+    """[n, dim] un-normalised rows; normalisation happens on the device at add / search time (K1).
+    hash_fn=None selects the native stable-hash embedder."""
+    if hash_fn is None:
+        return embed_texts_stable(texts, dim)
     out = np.zeros((len(texts), dim), dtype=np.float32)
     for i, t in enumerate(texts):
         out[i] = bag_of_hashed_words(t, dim, hash_fn)

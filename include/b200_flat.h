@@ -138,6 +138,12 @@ int b200_normalize_rows(float* x_host, int64_t n, int d, int device);
 int b200_merge_topk_dev(int metric, int G, int64_t nq, int64_t k, const float* D_parts_dev,
                         const int64_t* I_parts_dev, int64_t D_part_stride, int64_t I_part_stride,
                         float* D_out_dev, int64_t* I_out_dev, void* stream);
+/* Host-side bulk hashing-trick embedder (replaces the token loop of embed_text_hash,
+ * memo_cli.py:158-166) with CPython's str hash fixed to the PYTHONHASHSEED=0 key: n lower-cased
+ * UTF-8 texts concatenated in utf8, text i = [offsets[i], offsets[i+1]); out is [n,dim] float32
+ * un-normalised bucket counts.  b200_py_hash_seed0 is the token hash itself. */
+int b200_hash_embed(const char* utf8, const int64_t* offsets, int64_t n, int dim, float* out);
+int64_t b200_py_hash_seed0(const char* bytes, int64_t len);
 /* counter-based synthetic rows written to a device buffer [n,d] float32 */
 int b200_synth_rows_dev(float* out_dev, int64_t n, int d, uint64_t seed, int64_t first_row,
                         int normalize, void* stream);
