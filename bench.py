@@ -220,6 +220,7 @@ def main_b200(a):
     n, d, metric, store, normalize, k, nq = WORKLOADS[a.workload]
     idx = ShardedIndexFlat(d, metric, store=store, normalize=normalize)
     base = idx.local.index
+    fused = world > 1 and a.exchange == "fused" and idx.enable_fused_exchange()
     for name, val in (a.option or []):
         base.set_option(name, int(val))
     t0 = time.time()
@@ -256,7 +257,7 @@ def main_b200(a):
     ev[0].record()
     for s in range(a.steps):
         q = q_all[a.warmup + s]
-        if world == 1:
+        if world == 1 or fused:
             kev[s][0].record()
             idx.search_device(q, k)
             kev[s][1].record()
@@ -325,7 +326,9 @@ def main_b200(a):
                        "sharding": f"row-wise x{world}", "rows_per_gpu": hi - lo,
                        "l2_policy": "database >> 126 MB L2, distinct query per step; no flush needed",
                        "build_s": round(build_s, 3), "ids_consistent_host_vs_device": ok,
-                       "exchange": "none" if world == 1 else "NCCL all_gather of packed (I,D)[nq,k] + K4 merge kernel"},
+                       "exchange": "none" if world == 1 else (
+                           "fused: last CTA stores the local top-k into every peer's buffer over NVLink (CUDA IPC), flags, waits, merges"
+                           " — one kernel per GPU" if fused else "NCCL all_gather of packed (I,D)[nq,k] + K4 merge kernel")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "scan_topk_kernel", "bytes_per_launch": launch_bytes, "scan_launches_per_step": scans_per_step,
                          "note": "avg_launch_ms = CUDA-event time around the search on its stream / scan launches"
@@ -377,6 +380,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--option", nargs=2, action="append", metavar=("NAME", "VALUE"), help="native tuning option")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"], help="multi-GPU top-k exchange")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     if a.impl == "reference":

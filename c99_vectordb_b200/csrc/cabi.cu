@@ -17,6 +17,9 @@
 #include "rows.cuh"
 #include "scan_topk.cuh"
 
+// one (parity, sender) slot of the fused exchange: 16-byte header (epoch flag) + 8 queries x 256 results
+#define XCHG_SLOT_BYTES ((size_t)16 + (size_t)8 * B200_FUSED_K_MAX * 12)
+
 // ---------------------------------------------------------------------------------------------
 // errors
 // ---------------------------------------------------------------------------------------------
@@ -100,6 +103,12 @@ struct b200_index {
     uint8_t* up_pin[2] = {nullptr, nullptr};  // pinned upload ring for bulk host adds
     cudaEvent_t up_ev[2] = {nullptr, nullptr};
     size_t up_chunk = 0;
+    // fused multi-GPU exchange
+    uint8_t** xchg_peers_dev = nullptr;  // device array of world peer buffer pointers
+    int xchg_world = 0, xchg_rank = 0;
+    uint32_t xchg_epoch = 0;
+    int* xchg_status = nullptr;
+    bool xchg_active = false;            // the search in flight exchanges
     const uint32_t* cur_mask = nullptr;  // row bitmap of the search in flight (device), or null
     uint32_t* mask_dev = nullptr;        // staging for host masks
     size_t mask_cap = 0;
@@ -189,6 +198,8 @@ extern "C" int b200_index_destroy(b200_index* ix) {
         if (ix->up_pin[i]) cudaFreeHost(ix->up_pin[i]);
         if (ix->up_ev[i]) cudaEventDestroy(ix->up_ev[i]);
     }
+    cudaFree(ix->xchg_peers_dev);
+    cudaFree(ix->xchg_status);
     cudaFree(ix->mask_dev);
     cudaFree(ix->sh_rows);
     cudaFree(ix->sh_norm2);
@@ -690,6 +701,15 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     p.score_keys = score_keys;
     p.row_mask = ix->cur_mask;
     p.scratch_keys = pl.scratch_keys;
+    if (ix->xchg_active && !score_keys) {
+        p.xchg_peers = ix->xchg_peers_dev;
+        p.xchg_world = ix->xchg_world;
+        p.xchg_rank = ix->xchg_rank;
+        p.xchg_epoch = ++ix->xchg_epoch;
+        p.xchg_slot_bytes = (uint32_t)XCHG_SLOT_BYTES;
+        p.xchg_status = ix->xchg_status;
+        p.fused_tail = 1;  // the exchange lives in the last CTA's tail
+    }
     if (!score_keys) {
         size_t need = (size_t)pl.grid * pl.qb * k;
         CKI(grow(&ix->partials, &ix->partials_cap, need));
@@ -1067,7 +1087,7 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
     const bool fullrank = k >= ix->opt_fullrank_min_k || k > B200_FUSED_K_MAX;
     ix->stat_gemm_used = 0;
     if (!fullrank) {
-        if (!ix->cur_mask && gemm_eligible(ix, nq, k)) {
+        if (!ix->cur_mask && !ix->xchg_active && gemm_eligible(ix, nq, k)) {
             // K3 in blocks of at most 16384 queries (bounds the candidate scratch)
             for (int64_t q0 = 0; q0 < nq; q0 += 16384) {
                 int64_t nb = std::min<int64_t>(16384, nq - q0);
@@ -1179,6 +1199,73 @@ extern "C" int b200_index_search_masked(b200_index* ix, const float* q_host, int
     ix->cur_mask = ix->mask_dev;
     int rc = b200_index_search(ix, q_host, nq, k, D_host, I_host);
     ix->cur_mask = nullptr;
+    return rc;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// fused multi-GPU exchange
+// ---------------------------------------------------------------------------------------------
+extern "C" size_t b200_exchange_slot_bytes(void) { return XCHG_SLOT_BYTES; }
+
+extern "C" int b200_ipc_alloc(void** out_dev, size_t bytes, char handle_out[64]) {
+    if (!out_dev || !handle_out || bytes == 0) return fail("bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));
+    CK(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail("cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle_out, &h, 64);
+    *out_dev = p;
+    return 0;
+}
+extern "C" int b200_ipc_open(const char handle[64], void** out_dev) {
+    if (!handle || !out_dev) return fail("bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(cudaIpcOpenMemHandle(out_dev, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int b200_ipc_close(void* dev) {
+    if (dev) CK(cudaIpcCloseMemHandle(dev));
+    return 0;
+}
+extern "C" int b200_ipc_free(void* dev) {
+    if (dev) CK(cudaFree(dev));
+    return 0;
+}
+extern "C" int b200_index_set_exchange(b200_index* ix, int world, int rank, void* const* peer_bufs) {
+    if (!ix) return fail("null index");
+    if (world < 1 || world > 64 || rank < 0 || rank >= world || !peer_bufs) return fail("bad exchange topology");
+    CKI(use_device(ix));
+    CK(cudaStreamSynchronize(ix->stream));
+    if (ix->xchg_peers_dev) CK(cudaFree(ix->xchg_peers_dev));
+    ix->xchg_peers_dev = nullptr;
+    CK(cudaMalloc((void**)&ix->xchg_peers_dev, (size_t)world * sizeof(void*)));
+    CK(cudaMemcpy(ix->xchg_peers_dev, peer_bufs, (size_t)world * sizeof(void*), cudaMemcpyHostToDevice));
+    if (!ix->xchg_status) {
+        CK(cudaMalloc((void**)&ix->xchg_status, sizeof(int)));
+        CK(cudaMemset(ix->xchg_status, 0, sizeof(int)));
+    }
+    ix->xchg_world = world;
+    ix->xchg_rank = rank;
+    ix->xchg_epoch = 0;
+    return 0;
+}
+extern "C" int b200_index_search_exchange_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev,
+                                              int64_t* I_dev, void* stream) {
+    if (!ix) return fail("null index");
+    if (!ix->xchg_peers_dev) return fail("b200_index_set_exchange has not been called");
+    if (k > B200_FUSED_K_MAX || k >= ix->opt_fullrank_min_k) return fail("fused exchange needs k <= %d", B200_FUSED_K_MAX);
+    if (ix->ntotal == 0) return fail("fused exchange needs at least one row on every rank");
+    ix->xchg_active = true;
+    int rc = b200_index_search_dev(ix, q_dev, nq, k, D_dev, I_dev, stream);
+    ix->xchg_active = false;
     return rc;
 }
 

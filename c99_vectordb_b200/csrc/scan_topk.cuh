@@ -56,6 +56,13 @@ struct ScanParams {
     int evict_first;          // BULK: L2 evict-first hint on the stream
     uint32_t* score_keys;     // full-rank mode: [nqb, n] hi keys, else null
     const uint32_t* row_mask; // optional bitmap over rows (bit r of word r>>5): 0 = row excluded
+    // fused multi-GPU exchange (null = off): xchg_peers[g] is rank g's exchange buffer as mapped in
+    // this process (CUDA IPC peer mapping over NVLink); see exchange_and_merge()
+    uint8_t* const* xchg_peers;
+    int xchg_world, xchg_rank;
+    uint32_t xchg_epoch;      // strictly increasing per launch
+    uint32_t xchg_slot_bytes; // bytes of one (parity, sender) slot
+    int* xchg_status;         // set to 1 if a peer never showed up
     uint32_t scratch_keys;    // power of two >= max(warps*k, B200_FINAL_BUF_KEYS)
 };
 
@@ -202,10 +209,82 @@ __device__ __forceinline__ void final_merge_one(const ScanParams& p, int qi, uin
             uint32_t row = b200_key_row(key);
             id = p.id_map ? p.id_map[row] : (int64_t)row + p.id_base;
         }
-        p.D[(size_t)qi * k + i] = dist;
-        p.I[(size_t)qi * k + i] = id;
+        if (p.xchg_peers) {
+            // the local result goes straight into slot [parity][my rank] of EVERY rank's exchange
+            // buffer: posted stores over NVLink (and a plain store for the own buffer)
+            const size_t slot = ((size_t)(p.xchg_epoch & 1u) * p.xchg_world + p.xchg_rank) * p.xchg_slot_bytes;
+            const size_t off_i = 16 + ((size_t)qi * k + i) * 8;
+            const size_t off_d = 16 + (size_t)p.nqb * k * 8 + ((size_t)qi * k + i) * 4;
+            for (int g = 0; g < p.xchg_world; ++g) {
+                uint8_t* base = p.xchg_peers[g] + slot;
+                *reinterpret_cast<int64_t*>(base + off_i) = id;
+                *reinterpret_cast<float*>(base + off_d) = dist;
+            }
+        } else {
+            p.D[(size_t)qi * k + i] = dist;
+            p.I[(size_t)qi * k + i] = id;
+        }
     }
     __syncthreads();
+}
+
+// Fused multi-GPU top-k exchange, run by the last CTA of every rank's scan kernel after its local
+// results have been stored into all peers' buffers: publish (release, system scope) an epoch flag
+// in every peer's slot header, wait until all world flags of the OWN buffer carry this epoch, then
+// merge the world best-first lists per query with the K4 rank-by-counting rule (score best-first,
+// lower rank first, earlier position first) and write the final D/I.  Slots are double-buffered by
+// epoch parity: a rank cannot be two searches ahead of a peer because each search needs every
+// peer's flag.  Kernels on DIFFERENT GPUs wait on one another here — never two kernels of one GPU.
+template <int METRIC>
+__device__ __forceinline__ void exchange_and_merge(const ScanParams& p) {
+    const int k = p.k, G = p.xchg_world;
+    const size_t parity_base = (size_t)(p.xchg_epoch & 1u) * G * p.xchg_slot_bytes;
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < G) {
+        uint32_t* flag = reinterpret_cast<uint32_t*>(p.xchg_peers[threadIdx.x] + parity_base + (size_t)p.xchg_rank * p.xchg_slot_bytes);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(p.xchg_epoch) : "memory");
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(p.xchg_peers[p.xchg_rank] + parity_base + (size_t)threadIdx.x * p.xchg_slot_bytes);
+        const long long t0 = clock64();
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if (v != p.xchg_epoch && clock64() - t0 > 20000000000ll) {  // ~10 s: a peer is gone
+                *p.xchg_status = 1;
+                break;
+            }
+        } while (v != p.xchg_epoch);
+    }
+    __syncthreads();
+    const uint8_t* own = p.xchg_peers[p.xchg_rank] + parity_base;
+    const int total = G * p.nqb * k;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        const int q = t / (G * k), r = t - q * (G * k), g = r / k, j = r - g * k;
+        auto Iof = [&](int gg) { return reinterpret_cast<const int64_t*>(own + (size_t)gg * p.xchg_slot_bytes + 16) + (size_t)q * k; };
+        auto Dof = [&](int gg) { return reinterpret_cast<const float*>(own + (size_t)gg * p.xchg_slot_bytes + 16 + (size_t)p.nqb * k * 8) + (size_t)q * k; };
+        const int64_t id = __ldcv(Iof(g) + j);
+        const float sc = __ldcv(Dof(g) + j);
+        const uint32_t h = id < 0 ? 0u : b200_key_hi<METRIC>(sc);
+        int rank = j;
+        for (int g2 = 0; g2 < G; ++g2) {
+            if (g2 == g) continue;
+            const int64_t* I2 = Iof(g2);
+            const float* D2 = Dof(g2);
+            int lo = 0, hi = k;  // entries of list g2 that precede this candidate
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                int64_t im = __ldcv(I2 + mid);
+                uint32_t hm = im < 0 ? 0u : b200_key_hi<METRIC>(__ldcv(D2 + mid));
+                bool before = (g2 < g) ? (hm >= h) : (hm > h);
+                if (before) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) {
+            p.D[(size_t)q * k + rank] = id < 0 ? ((METRIC == 0) ? -FLT_MAX : FLT_MAX) : sc;
+            p.I[(size_t)q * k + rank] = id < 0 ? (int64_t)-1 : id;
+        }
+    }
 }
 
 // One CTA per query: the final merge as its own launch, used when a scan launch carries several
@@ -504,8 +583,10 @@ scan_topk_kernel(const ScanParams p) {
     __syncthreads();
     if (!s_is_last) return;
     __threadfence();
-    if (!fullrank && p.fused_tail)
+    if (!fullrank && p.fused_tail) {
         for (int qi = 0; qi < p.nqb; ++qi) final_merge_one<METRIC, QB>(p, qi, gridDim.x, scratch, sctr);
+        if (p.xchg_peers) exchange_and_merge<METRIC>(p);
+    }
     if (threadIdx.x == 0) {  // ready for the next launch on this stream
         p.ticket[0] = 0u;
         p.ticket[1] = 0u;

@@ -65,6 +65,8 @@ class ShardedIndexFlat:
         self.ntotal_global = 0
         self.merge_launches = 0
         self._bufs = {}
+        self._fused = False
+        self._xchg_ptrs = []
 
     # ---- add --------------------------------------------------------------------------------
     def add_with_ids(self, x: np.ndarray, ids: np.ndarray) -> None:
@@ -101,6 +103,42 @@ class ShardedIndexFlat:
         base = getattr(self.local, "index", self.local)
         return int(getattr(base, "launch_count", 0)) + self.merge_launches
 
+    # ---- fused exchange -----------------------------------------------------------------------
+    def enable_fused_exchange(self) -> bool:
+        """Switch the top-k exchange from NCCL all-gather + K4 to the fused form: the scan kernel's
+        last CTA stores its local result into every rank's exchange buffer over NVLink (CUDA IPC peer
+        mappings), flags it, waits for the peers and merges — one kernel per GPU per search.
+        Collective: every rank must call it.  Returns False (and keeps NCCL) on a single rank."""
+        import torch.distributed as dist
+
+        if self.world == 1 or self.device.type != "cuda":
+            return False
+        L = _cabi.load()
+        nbytes = 2 * self.world * int(L.b200_exchange_slot_bytes())
+        handle = C.create_string_buffer(64)
+        mine = C.c_void_p()
+        _cabi.check(L.b200_ipc_alloc(C.byref(mine), nbytes, handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=self.group)
+        peers = (C.c_void_p * self.world)()
+        for g in range(self.world):
+            if g == self.rank:
+                peers[g] = mine.value
+            else:
+                p = C.c_void_p()
+                _cabi.check(L.b200_ipc_open(handles[g], C.byref(p)))
+                peers[g] = p.value
+        self._xchg_ptrs = [peers[g] for g in range(self.world)]
+        _cabi.check(L.b200_index_set_exchange(self.local.index._h, self.world, self.rank, peers))
+        dist.barrier(group=self.group)
+        self._fused = True
+        return True
+
+    def _fused_ok(self, k: int) -> bool:
+        # every rank must hold rows (an empty shard launches no kernel and nobody would flag for it)
+        lo, hi = shard_range(self.ntotal_global, self.world, self.world - 1)
+        return self._fused and k <= 256 and hi > lo
+
     # ---- search -----------------------------------------------------------------------------
     def _buffers(self, nq: int, k: int):
         import torch
@@ -122,6 +160,12 @@ class ShardedIndexFlat:
         import torch.distributed as dist
 
         nq, k = int(q.shape[0]), int(k)
+        if self._fused_ok(k):
+            _, _, D, I, _, _ = self._buffers(nq, k)
+            stream = torch.cuda.current_stream(self.device).cuda_stream or 1
+            _cabi.check(_cabi.load().b200_index_search_exchange_dev(
+                self.local.index._h, q.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(), C.c_void_p(stream)))
+            return D, I
         mine, gathered, D, I, nbytes, off_d = self._buffers(nq, k)
         I_loc = mine[: nq * k * 8].view(torch.int64).view(nq, k)
         D_loc = mine[off_d: off_d + nq * k * 4].view(torch.float32).view(nq, k)

@@ -106,6 +106,24 @@ int b200_index_search_masked(b200_index* ix, const float* q_host, int64_t nq, in
                              const uint32_t* mask_host, float* D_host, int64_t* I_host);
 int b200_index_search_masked_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k,
                                  const uint32_t* mask_dev, float* D_dev, int64_t* I_dev, void* stream);
+/* ---- fused multi-GPU exchange (one process per GPU) --------------------------------------------
+ * Instead of an NCCL all-gather + merge kernel, the scan kernel's last CTA stores its local top-k
+ * into every rank's exchange buffer over NVLink peer mappings, flags it, waits for the peers and
+ * merges: scan + exchange + merge are ONE kernel per GPU.
+ *   b200_ipc_alloc   device buffer (zeroed) + its 64-byte CUDA IPC handle, to be shared with peers
+ *   b200_ipc_open    map a peer's handle into this process (enables peer access lazily)
+ *   b200_index_set_exchange   peer_bufs[g] = rank g's buffer as mapped here (own buffer for g=rank);
+ *                    every buffer holds 2 * world * b200_exchange_slot_bytes() bytes
+ *   b200_index_search_exchange_dev   like search_dev for nq <= 8 per launch group and k <= 256, but
+ *                    D/I receive the GLOBAL merged result; every rank must call it for every search */
+int b200_ipc_alloc(void** out_dev, size_t bytes, char handle_out[64]);
+int b200_ipc_open(const char handle[64], void** out_dev);
+int b200_ipc_close(void* dev);
+int b200_ipc_free(void* dev);
+size_t b200_exchange_slot_bytes(void);
+int b200_index_set_exchange(b200_index* ix, int world, int rank, void* const* peer_bufs);
+int b200_index_search_exchange_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k,
+                                   float* D_dev, int64_t* I_dev, void* stream);
 /* kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t b200_index_launch_count(b200_index* ix);
 /* block until the handle's stream is idle */

@@ -54,6 +54,17 @@ def _worker(rank, world, port, out_dir):
         Dw, Iw = oracle.search(1, oracle.synth_rows(300_000, 384, 1234), q, 10, order=oracle.ORDER_DEVICE)
         np.testing.assert_array_equal(I, Iw)
         np.testing.assert_array_equal(D, Dw)
+        # fused exchange: the scan kernel stores into the peers' buffers over NVLink and merges itself
+        assert idx.enable_fused_exchange()
+        for nq, k in ((1, 10), (3, 10), (8, 100), (11, 7)):
+            q = oracle.synth_rows(nq, 384, 999 + nq)
+            Df, If = idx.search(q, k)
+            Dw, Iw = oracle.search(1, oracle.synth_rows(300_000, 384, 1234), q, k, order=oracle.ORDER_DEVICE)
+            np.testing.assert_array_equal(If, Iw)
+            np.testing.assert_array_equal(Df, Dw)
+        for rep in range(20):  # back-to-back searches exercise the double-buffered slots
+            Df2, If2 = idx.search(q, k)
+            np.testing.assert_array_equal(If2, Iw)
         np.save(os.path.join(out_dir, f"ok_{rank}.npy"), I)
     finally:
         dist.destroy_process_group()
