@@ -20,7 +20,8 @@
 //      are re-run through the exact scan kernel.
 //
 // Warp roles (6 warps): 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..5 = epilogue
-// (warp w reads TMEM lanes 32*(w%4)..+31: one query per thread).
+// (warp w reads TMEM lanes 32*(w%4)..+31: one query per thread).  CG = 2 pairs two CTAs (SMs) on one
+// 256 x 256 tile with cta_group::2; see gemm_topk_kernel.
 #pragma once
 #include <cuda.h>
 
@@ -30,12 +31,8 @@
 #define G3_BLOCK_N 256
 #define G3_BLOCK_K 64   // bf16 elements = 128 bytes = one swizzle atom row
 #define G3_UMMA_K 16
-#define G3_STAGES 4
 #define G3_THREADS 192
 #define G3_A_BYTES (G3_BLOCK_M * G3_BLOCK_K * 2)
-#define G3_B_BYTES (G3_BLOCK_N * G3_BLOCK_K * 2)
-#define G3_STAGE_BYTES (G3_A_BYTES + G3_B_BYTES)
-#define G3_SMEM_BYTES (G3_STAGES * G3_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 #define G3_MODE_TILEMAX 0
 #define G3_MODE_EMIT 1
 
@@ -65,13 +62,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-__device__ __forceinline__ void tc_alloc(uint32_t smem_dst, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

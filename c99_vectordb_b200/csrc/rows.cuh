@@ -17,14 +17,6 @@ struct IngestParams {
     int d_pad;             // destination elements per row (zero padded)
 };
 
-template <int STORE>
-__device__ __forceinline__ void store_elem(uint8_t* row, int col, float v) {
-    if (STORE == 0)
-        reinterpret_cast<float*>(row)[col] = v;
-    else
-        reinterpret_cast<__nv_bfloat16*>(row)[col] = __float2bfloat16_rn(v);
-}
-
 template <int STORE, int NORMALIZE, int VEC>
 __global__ void __launch_bounds__(256) ingest_rows_kernel(const IngestParams p) {
     const int lane = threadIdx.x & 31;

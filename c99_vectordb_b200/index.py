@@ -29,8 +29,6 @@ from . import _cabi
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
 
-_FLT_MAX = float(np.finfo(np.float32).max)
-
 
 def _default_device() -> int:
     for var in ("B200_DEVICE", "LOCAL_RANK"):
@@ -157,6 +155,19 @@ class IndexFlat(Index):
 
     def add_with_ids(self, x, ids) -> None:
         raise RuntimeError("add_with_ids not implemented for this type of index")  # as faiss [upstream]
+
+    def add_device(self, x, ids=None) -> None:
+        """Rows (and optional int64 ids) already resident on this index's GPU as torch tensors:
+        K1 ingests them without touching the host (b200_index_add_dev)."""
+        import torch
+
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2 and x.shape[1] == self.d
+        idp = None
+        if ids is not None:
+            assert ids.is_cuda and ids.dtype == torch.int64 and ids.is_contiguous() and ids.shape == (x.shape[0],)
+            idp = ids.data_ptr()
+        torch.cuda.current_stream(x.device).synchronize()  # the handle's stream must see finished producers
+        _cabi.check(_cabi.load().b200_index_add_dev(self._h, x.data_ptr(), x.shape[0], idp, int(self.normalize)))
 
     def _add_with_ids(self, x, ids) -> None:
         x = self._coerce_x(x)

@@ -4,8 +4,9 @@ The reference has no distributed code (single process, memo_cli.py:883-949); thi
 restatement north_star specifies for index.search (memo_cli.py:292): rows are split into contiguous
 ranges, rank g owning [g*ceil(N/G), (g+1)*ceil(N/G)); every rank runs the scan kernel over its
 shard (ids are translated to GLOBAL record ids inside the kernel), the per-rank best-first lists
-are exchanged with ONE all-gather of a packed (I,D) buffer (NCCL over NVLink/NVSwitch), and the K4
-kernel merges them on every rank.  Contiguous ranges make "lower rank first, then earlier list
+are exchanged either inside the scan kernel itself (fused: peer-memory stores over NVLink + flags +
+in-kernel merge, enable_fused_exchange) or with ONE NCCL all-gather of a packed (I,D) buffer followed
+by the K4 merge kernel on every rank.  Contiguous ranges make "lower rank first, then earlier list
 position" equal to the global tie rule (smaller row position first).
 
 torch is plumbing only: device buffers, the stream, and the process group.
@@ -66,7 +67,6 @@ class ShardedIndexFlat:
         self.merge_launches = 0
         self._bufs = {}
         self._fused = False
-        self._xchg_ptrs = []
 
     # ---- add --------------------------------------------------------------------------------
     def add_with_ids(self, x: np.ndarray, ids: np.ndarray) -> None:
@@ -128,7 +128,6 @@ class ShardedIndexFlat:
                 p = C.c_void_p()
                 _cabi.check(L.b200_ipc_open(handles[g], C.byref(p)))
                 peers[g] = p.value
-        self._xchg_ptrs = [peers[g] for g in range(self.world)]
         _cabi.check(L.b200_index_set_exchange(self.local.index._h, self.world, self.rank, peers))
         dist.barrier(group=self.group)
         self._fused = True
