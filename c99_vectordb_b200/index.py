@@ -403,8 +403,38 @@ def _read_any(f, device):
     return base
 
 
+def _skip_vector(f, elem_bytes: int, limit: int) -> int:
+    n, = struct.unpack("<Q", _read_exact(f, 8))
+    if n > limit:
+        raise RuntimeError("implausible vector length in index file")
+    f.seek(n * elem_bytes, os.SEEK_CUR)
+    return n
+
+
+def _skip_hnsw_graph(f, ntotal: int) -> None:
+    """memo's original files are IndexIDMap2 -> IndexHNSWFlat ("IHNf", memo_cli.py:244-248): header,
+    the HNSW graph, then the flat storage index.  The graph is useless for an exact flat index, so
+    it is skipped: assign_probas (double), cum_nneighbor_per_level (int32), levels (int32, one per
+    vector), offsets (size_t, ntotal+1), neighbors (int32), then entry_point, max_level,
+    efConstruction, efSearch, upper_beam (5 x int32) [upstream write_HNSW layout, unverified here —
+    every size is checked and a mismatch raises, which memo treats as an unreadable file]."""
+    big = 1 << 40
+    _skip_vector(f, 8, 1 << 16)
+    _skip_vector(f, 4, 1 << 16)
+    if _skip_vector(f, 4, big) != ntotal:
+        raise RuntimeError("HNSW levels do not match ntotal")
+    if _skip_vector(f, 8, big) != ntotal + 1:
+        raise RuntimeError("HNSW offsets do not match ntotal")
+    _skip_vector(f, 4, big)
+    _read_exact(f, 20)
+
+
 def _read_flat_payload(f, device):
     fourcc = _read_exact(f, 4)
+    if fourcc == b"IHNf":
+        _d, ntotal, _metric = _read_header(f)
+        _skip_hnsw_graph(f, ntotal)
+        fourcc = _read_exact(f, 4)  # the storage index
     if fourcc not in (b"IxFI", b"IxF2", b"IxFl"):
         raise RuntimeError(f"Index type {fourcc!r} not recognized")
     d, ntotal, metric = _read_header(f)

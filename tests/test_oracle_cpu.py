@@ -146,3 +146,22 @@ def test_adapter_golden_is_self_consistent():
     D, I = oracle.search(oracle.METRIC_L2, vecs, g["qvecs"], len(kept), ids=kept)
     np.testing.assert_array_equal(I, g["res_ids"])
     np.testing.assert_array_equal(D, g["res_scores"])
+
+
+@pytest.mark.parametrize("metric", [oracle.METRIC_IP, oracle.METRIC_L2])
+def test_oracle_against_independent_sklearn_bruteforce(metric):
+    """faiss is not installable here, so as a second independent implementation the oracle's ids are
+    checked against scikit-learn's exact brute-force k-NN (float64) on well separated random data."""
+    sk = pytest.importorskip("sklearn.neighbors")
+    n, d, k, nq = 5000, 64, 10, 20
+    db = oracle.normalize_rows(oracle.synth_rows(n, d, 41))
+    q = oracle.normalize_rows(oracle.synth_rows(nq, d, 42))
+    D, I = oracle.search(metric, db, q, k)
+    # on unit vectors L2-ascending and IP-descending rankings coincide (SURVEY.md §0.3)
+    nn = sk.NearestNeighbors(n_neighbors=k, algorithm="brute", metric="euclidean").fit(db.astype(np.float64))
+    dist, ind = nn.kneighbors(q.astype(np.float64))
+    np.testing.assert_array_equal(I, ind)
+    if metric == oracle.METRIC_L2:
+        np.testing.assert_allclose(D, dist ** 2, rtol=1e-5, atol=1e-6)
+    else:
+        np.testing.assert_allclose(D, 1.0 - dist ** 2 / 2.0, rtol=1e-5, atol=1e-6)

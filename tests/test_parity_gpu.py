@@ -419,3 +419,42 @@ def test_filtered_recall_against_reference_command_recall(b200):
                 start = i
         got_all = ma.search_filtered(idx, qvec[qtext], len(g["kept"]), elig[f].tolist())
         assert sorted(r.doc_id for r in got_all) == sorted(elig[f].tolist())
+
+
+def test_read_index_imports_memo_hnsw_files(b200, tmp_path):
+    """A file laid out like faiss writes IndexIDMap2(IndexHNSWFlat) (memo_cli.py:244-248, :361): the
+    graph is skipped and the flat storage + id map become an exact flat index."""
+    import struct
+
+    d, n = 384, 50
+    db = oracle.normalize_rows(oracle.synth_rows(n, d, 3))
+    ids = np.arange(n, dtype=np.int64) * 2
+
+    def header(ntotal, metric=1):
+        return struct.pack("<iqqqBi", d, ntotal, 1 << 20, 1 << 20, 1, metric)
+
+    def vec(arr):
+        return struct.pack("<Q", len(arr)) + arr.tobytes()
+
+    levels = np.ones(n, dtype=np.int32)
+    offsets = np.arange(n + 1, dtype=np.uint64) * 64
+    neighbors = np.full(n * 64, -1, dtype=np.int32)
+    blob = b"IxM2" + header(n)
+    blob += b"IHNf" + header(n)
+    blob += vec(np.array([0.9, 0.1], dtype=np.float64)) + vec(np.array([0, 64, 96], dtype=np.int32))
+    blob += vec(levels) + vec(offsets) + vec(neighbors) + struct.pack("<5i", 0, 0, 200, 64, 1)
+    blob += b"IxF2" + header(n) + struct.pack("<Q", n * d) + db.tobytes()
+    blob += struct.pack("<Q", n) + ids.tobytes()
+    p = tmp_path / "legacy.memo"
+    p.write_bytes(blob)
+    idx = b200.read_index(str(p))
+    assert isinstance(idx, b200.IndexIDMap2) and idx.ntotal == n
+    np.testing.assert_array_equal(b200.vector_to_array(idx.id_map), ids)
+    q = oracle.normalize_rows(oracle.synth_rows(1, d, 4))
+    D, I = idx.search(q, n)
+    Dw, Iw = oracle.search(1, db, q, n, ids=ids, order=oracle.ORDER_DEVICE)
+    np.testing.assert_array_equal(I, Iw)
+    # a truncated graph section must raise (memo then starts a fresh index, memo_cli.py:254-257)
+    p.write_bytes(blob[:200])
+    with pytest.raises(Exception):
+        b200.read_index(str(p))
