@@ -810,12 +810,18 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uin
 }
 
 static bool gemm_eligible(b200_index* ix, int64_t nq, int64_t k) {
-    return ix->opt_gemm_min_nq > 0 && nq >= ix->opt_gemm_min_nq && ix->metric == B200_METRIC_IP && k <= B200_FUSED_K_MAX &&
+    return ix->opt_gemm_min_nq > 0 && nq >= ix->opt_gemm_min_nq && k <= B200_FUSED_K_MAX &&
            ix->ntotal >= 65536 && ix->ntotal >= 1024 * k && ix->d >= 32 && k < ix->opt_fullrank_min_k;
 }
 
+// K of the shadow GEMM: d (+2 columns carrying |y|^2/2 and -1 for L2), padded to whole 64-column blocks
+static int gemm_kpad(const b200_index* ix) {
+    const int cols = ix->d + (ix->metric == B200_METRIC_L2 ? 2 : 0);
+    return (cols + G3_BLOCK_K - 1) / G3_BLOCK_K * G3_BLOCK_K;
+}
+
 static int ensure_shadow(b200_index* ix, cudaStream_t st) {
-    const int kpad = (ix->d + G3_BLOCK_K - 1) / G3_BLOCK_K * G3_BLOCK_K;
+    const int kpad = gemm_kpad(ix);
     if (ix->sh_valid_rows == ix->ntotal) return 0;
     if (ix->sh_cap_rows < (size_t)ix->ntotal) {
         CK(cudaStreamSynchronize(st));
@@ -837,7 +843,8 @@ static int ensure_shadow(b200_index* ix, cudaStream_t st) {
     if (!ix->sh_maxnorm) CK(cudaMalloc((void**)&ix->sh_maxnorm, sizeof(unsigned int)));
     CK(cudaMemsetAsync(ix->sh_maxnorm, 0, sizeof(unsigned int), st));
     shadow_rows_kernel<<<ix->num_sms * 8, 256, 0, st>>>(ix->rows, ix->pitch, ix->store, (uint64_t)ix->ntotal, ix->d, kpad,
-                                                        ix->sh_rows, ix->sh_norm2, ix->sh_maxnorm);
+                                                        ix->metric == B200_METRIC_L2 ? 1 : 0, ix->sh_rows, ix->sh_norm2,
+                                                        ix->sh_maxnorm);
     ++ix->launches;
     CK(cudaGetLastError());
     ix->sh_valid_rows = ix->ntotal;
@@ -849,7 +856,7 @@ static int search_scan_block(b200_index* ix, const float* q_dev, int64_t nq, int
 
 static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev, int64_t* I_dev,
                        cudaStream_t st) {
-    const int kpad = (ix->d + G3_BLOCK_K - 1) / G3_BLOCK_K * G3_BLOCK_K;
+    const int kpad = gemm_kpad(ix);
     const uint64_t n = (uint64_t)ix->ntotal;
     const uint32_t NT = (uint32_t)((n + G3_BLOCK_N - 1) / G3_BLOCK_N);
     const uint32_t m_tiles = (uint32_t)((nq + G3_BLOCK_M - 1) / G3_BLOCK_M);
@@ -880,7 +887,8 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     // ---- query shadow (zero padded to whole 128-query tiles) ----
     CK(cudaMemsetAsync(ix->g_qb, 0, qb_elems * sizeof(__nv_bfloat16), st));
     shadow_rows_kernel<<<(unsigned)std::min<int64_t>((nq + 7) / 8, ix->num_sms * 8), 256, 0, st>>>(
-        (const uint8_t*)q_dev, (uint64_t)ix->d * 4, 0, (uint64_t)nq, ix->d, kpad, ix->g_qb, ix->g_qnorm2, nullptr);
+        (const uint8_t*)q_dev, (uint64_t)ix->d * 4, 0, (uint64_t)nq, ix->d, kpad, ix->metric == B200_METRIC_L2 ? 2 : 0,
+        ix->g_qb, ix->g_qnorm2, nullptr);
     ++ix->launches;
     CK(cudaGetLastError());
     CUtensorMap tm_q, tm_db;
@@ -992,7 +1000,11 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     rp.certified = ix->g_cert;
     const size_t rsmem = (size_t)rp.qstride * 4 + (size_t)cap * 8;
     CK(cudaFuncSetAttribute(rerank_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-    rerank_kernel<0><<<(unsigned)nq, 256, rsmem, st>>>(rp);
+    CK(cudaFuncSetAttribute(rerank_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    if (ix->metric == B200_METRIC_IP)
+        rerank_kernel<0><<<(unsigned)nq, 256, rsmem, st>>>(rp);
+    else
+        rerank_kernel<1><<<(unsigned)nq, 256, rsmem, st>>>(rp);
     ++ix->launches;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev[3], st));

@@ -398,8 +398,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 // ---- shadow copies --------------------------------------------------------------------------------
 // fp32 rows (pitch bytes) -> bf16 K-major rows of kpad elements (zero padded) + fp32 squared norms
 // + a running maximum of the row norm (for the certificate's error bound).
+// aug: 0 = none; 1 = database row for L2: columns d, d+1 hold h = |y|^2 / 2 split into two bf16
+// (hi + lo, residual <= 2^-16 h); 2 = query for L2: columns d, d+1 hold -1.  With these the same
+// GEMM yields q.y - |y|^2/2 = (|q|^2 - L2) / 2: larger is better, exactly like IP.
 __global__ void __launch_bounds__(256)
-shadow_rows_kernel(const uint8_t* __restrict__ rows, uint64_t pitch, int store, uint64_t n, int d, int kpad,
+shadow_rows_kernel(const uint8_t* __restrict__ rows, uint64_t pitch, int store, uint64_t n, int d, int kpad, int aug,
                    __nv_bfloat16* __restrict__ out, float* __restrict__ norm2, unsigned int* __restrict__ max_norm2_bits) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -416,7 +419,19 @@ shadow_rows_kernel(const uint8_t* __restrict__ rows, uint64_t pitch, int store, 
             dst[c] = __float2bfloat16_rn(v);
         }
         acc = warp_sum_xor(acc);
-        if (lane == 0 && norm2) norm2[r] = acc;
+        __syncwarp();
+        if (lane == 0) {
+            if (norm2) norm2[r] = acc;
+            if (aug == 1) {
+                const float h = 0.5f * acc;
+                const __nv_bfloat16 hi = __float2bfloat16_rn(h);
+                dst[d] = hi;
+                dst[d + 1] = __float2bfloat16_rn(h - __bfloat162float(hi));
+            } else if (aug == 2) {
+                dst[d] = __float2bfloat16_rn(-1.0f);
+                dst[d + 1] = __float2bfloat16_rn(-1.0f);
+            }
+        }
         wmax = fmaxf(wmax, acc);
     }
     if (lane == 0 && max_norm2_bits) atomicMax(max_norm2_bits, __float_as_uint(wmax));  // non-negative floats order as uints
@@ -496,26 +511,24 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
         float acc = 0.0f;
         for (uint32_t ch = lane; ch < p.nvec; ch += 32) {
             uint4 raw = ldg_nc_v4(rp + (size_t)ch * 16);
+            auto step = [&](uint32_t bits, float qv) {  // same element arithmetic as scan_topk.cuh acc1<>
+                const float v = __uint_as_float(bits);
+                if (METRIC == 0) {
+                    acc = fmaf(v, qv, acc);
+                } else {
+                    const float t = v - qv;
+                    acc = fmaf(t, t, acc);
+                }
+            };
             if (p.store == 0) {
                 float4 qv = q4[ch];
-                if (METRIC == 0) {
-                    acc = fmaf(__uint_as_float(raw.x), qv.x, acc);
-                    acc = fmaf(__uint_as_float(raw.y), qv.y, acc);
-                    acc = fmaf(__uint_as_float(raw.z), qv.z, acc);
-                    acc = fmaf(__uint_as_float(raw.w), qv.w, acc);
-                }
+                step(raw.x, qv.x); step(raw.y, qv.y); step(raw.z, qv.z); step(raw.w, qv.w);
             } else {
                 float4 qa = q4[2 * ch], qb = q4[2 * ch + 1];
-                if (METRIC == 0) {
-                    acc = fmaf(__uint_as_float(raw.x << 16), qa.x, acc);
-                    acc = fmaf(__uint_as_float(raw.x & 0xffff0000u), qa.y, acc);
-                    acc = fmaf(__uint_as_float(raw.y << 16), qa.z, acc);
-                    acc = fmaf(__uint_as_float(raw.y & 0xffff0000u), qa.w, acc);
-                    acc = fmaf(__uint_as_float(raw.z << 16), qb.x, acc);
-                    acc = fmaf(__uint_as_float(raw.z & 0xffff0000u), qb.y, acc);
-                    acc = fmaf(__uint_as_float(raw.w << 16), qb.z, acc);
-                    acc = fmaf(__uint_as_float(raw.w & 0xffff0000u), qb.w, acc);
-                }
+                step(raw.x << 16, qa.x); step(raw.x & 0xffff0000u, qa.y);
+                step(raw.y << 16, qa.z); step(raw.y & 0xffff0000u, qa.w);
+                step(raw.z << 16, qb.x); step(raw.z & 0xffff0000u, qb.y);
+                step(raw.w << 16, qb.z); step(raw.w & 0xffff0000u, qb.w);
             }
         }
         acc = warp_sum_xor(acc);
@@ -561,10 +574,19 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
             if (kth == 0ull) {
                 ok = false;
             } else {
-                float maxn = sqrtf(__uint_as_float(*p.max_norm2_bits));
-                float eps = p.eps_rel * sqrtf(p.qnorm2[qi]) * maxn;
-                float bound = p.theta[qi] + eps;
-                ok = b200_key_score(kth, METRIC) > bound;
+                const float maxn = sqrtf(__uint_as_float(*p.max_norm2_bits));
+                const float qn2 = p.qnorm2[qi], qn = sqrtf(qn2);
+                const float eps = p.eps_rel * qn * maxn;
+                if (METRIC == 0) {
+                    ok = b200_key_score(kth, METRIC) > p.theta[qi] + eps;
+                } else {
+                    // the GEMM ranks a = q.y - |y|^2/2 = (|q|^2 - L2)/2; a row that was not emitted has
+                    // a <= theta + eps_a, i.e. L2 >= |q|^2 - 2 (theta + eps_a).  eps_a adds the hi/lo split
+                    // residual of |y|^2/2; slack covers the fp32 rounding of |q|^2 and of both L2 sums.
+                    const float eps_a = eps + 2e-5f * maxn * maxn;
+                    const float slack = 4.0f * (float)p.d * 6e-8f * (qn + maxn) * (qn + maxn);
+                    ok = b200_key_score(kth, METRIC) < qn2 - 2.0f * (p.theta[qi] + eps_a) - slack;
+                }
             }
         }
         p.certified[qi] = ok ? 1 : 0;

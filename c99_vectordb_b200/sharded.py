@@ -133,10 +133,12 @@ class ShardedIndexFlat:
         self._fused = True
         return True
 
-    def _fused_ok(self, k: int) -> bool:
-        # every rank must hold rows (an empty shard launches no kernel and nobody would flag for it)
+    def _fused_ok(self, nq: int, k: int) -> bool:
+        # The fused exchange lives in the scan kernel's tail: one launch per block of <= 8 queries.
+        # Larger batches go through NCCL so that every shard can use the tensor-core path (K3).
+        # Every rank must hold rows (an empty shard launches no kernel and nobody would flag for it).
         lo, hi = shard_range(self.ntotal_global, self.world, self.world - 1)
-        return self._fused and k <= 256 and hi > lo
+        return self._fused and nq <= 8 and k <= 256 and hi > lo
 
     # ---- search -----------------------------------------------------------------------------
     def _buffers(self, nq: int, k: int):
@@ -159,7 +161,7 @@ class ShardedIndexFlat:
         import torch.distributed as dist
 
         nq, k = int(q.shape[0]), int(k)
-        if self._fused_ok(k):
+        if self._fused_ok(nq, k):
             _, _, D, I, _, _ = self._buffers(nq, k)
             stream = torch.cuda.current_stream(self.device).cuda_stream or 1
             _cabi.check(_cabi.load().b200_index_search_exchange_dev(

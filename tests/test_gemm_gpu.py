@@ -16,7 +16,7 @@ def b200(gpu):
     return m
 
 
-def run_case(m, n, d, nq, k, store="f32", normalize=False, dup=False, ids=False, **opts):
+def run_case(m, n, d, nq, k, store="f32", normalize=False, dup=False, ids=False, metric=0, **opts):
     db = oracle.synth_rows(n, d, 1234)
     if dup:
         db[n // 2: n // 2 + 1000] = db[:1000]  # exact ties across tiles
@@ -24,7 +24,7 @@ def run_case(m, n, d, nq, k, store="f32", normalize=False, dup=False, ids=False,
     if normalize:
         db = oracle.normalize_rows(db, oracle.ORDER_DEVICE)
         q = oracle.normalize_rows(q, oracle.ORDER_DEVICE)
-    base = m.IndexFlat(d, 0, store=store)
+    base = m.IndexFlat(d, metric, store=store)
     base.set_option("gemm_min_nq", 32)
     for name, v in opts.items():
         base.set_option(name, v)
@@ -39,7 +39,7 @@ def run_case(m, n, d, nq, k, store="f32", normalize=False, dup=False, ids=False,
         idx = base
     D, I = idx.search(q, k)
     ref_db = oracle.round_bf16(db) if store == "bf16" else db
-    Dw, Iw = oracle.search(0, ref_db, q, k, ids=idv, order=oracle.ORDER_DEVICE, chunk=8 if store == "bf16" else 4)
+    Dw, Iw = oracle.search(metric, ref_db, q, k, ids=idv, order=oracle.ORDER_DEVICE, chunk=8 if store == "bf16" else 4)
     stats = {s: base.get_option(s) for s in ("stat_gemm_used", "stat_gemm_fallbacks", "stat_gemm_cand_total",
                                              "stat_gemm_pass1_us", "stat_gemm_pass2_us", "stat_gemm_rerank_us")}
     np.testing.assert_array_equal(I, Iw, err_msg=str(stats))
@@ -84,3 +84,17 @@ def test_small_batches_do_not_use_gemm(b200):
     idx.add(db)
     idx.search(q, 5)
     assert idx.get_option("stat_gemm_used") == 0
+
+
+@pytest.mark.parametrize("n,d,nq,k,normalize", [(120_000, 384, 100, 10, True), (200_000, 768, 130, 100, False),
+                                                  (90_000, 100, 64, 5, False), (150_000, 62, 70, 10, True)])
+def test_batched_l2_exact(b200, n, d, nq, k, normalize):
+    """memo's default metric (squared L2): the GEMM ranks q.y - |y|^2/2 through two extra K columns."""
+    st = run_case(b200, n, d, nq, k, metric=1, normalize=normalize, dup=True, ids=True)
+    assert st["stat_gemm_used"] == 1
+    assert st["stat_gemm_fallbacks"] <= nq // 4, st
+
+
+def test_batched_l2_bf16_store(b200):
+    st = run_case(b200, 100_000, 512, 80, 10, metric=1, store="bf16")
+    assert st["stat_gemm_used"] == 1

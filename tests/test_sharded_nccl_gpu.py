@@ -62,6 +62,14 @@ def _worker(rank, world, port, out_dir):
             Dw, Iw = oracle.search(1, oracle.synth_rows(300_000, 384, 1234), q, k, order=oracle.ORDER_DEVICE)
             np.testing.assert_array_equal(If, Iw)
             np.testing.assert_array_equal(Df, Dw)
+        # a large batch: every shard runs the tensor-core path (K3), results merged through NCCL + K4
+        idx.local.index.set_option("gemm_min_nq", 32)
+        qb = oracle.synth_rows(70, 384, 4242)
+        Db, Ib = idx.search(qb, 10)
+        assert idx.local.index.get_option("stat_gemm_used") == 1
+        Dw2, Iw2 = oracle.search(1, oracle.synth_rows(300_000, 384, 1234), qb, 10, order=oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(Ib, Iw2)
+        np.testing.assert_array_equal(Db, Dw2)
         for rep in range(20):  # back-to-back searches exercise the double-buffered slots
             Df2, If2 = idx.search(q, k)
             np.testing.assert_array_equal(If2, Iw)
