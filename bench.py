@@ -346,6 +346,21 @@ def main_b200(a):
                 line["roofline"]["traffic"] = tr
         except Exception:
             pass
+        if store == "bf16" and world == 1:
+            # bf16 storage is lossy: report recall@k against the same rows stored in fp32 (north_star)
+            ref = m.IndexFlat(d, metric, normalize=normalize)
+            ref.add_synthetic(n, DB_SEED)
+            hits = tot = 0
+            for s in range(min(total_steps, 50)):
+                _, I16 = idx.search_device(q_all[s], k)
+                _, I32 = ref.search_device(q_all[s], k)
+                torch.cuda.synchronize()
+                a16, a32 = I16.cpu().numpy(), I32.cpu().numpy()
+                for r in range(nq):
+                    hits += len(set(a16[r].tolist()) & set(a32[r].tolist()))
+                    tot += k
+            line["config"][f"recall_at_{k}_vs_fp32_rows"] = hits / tot
+            ref.close()
         if gemm_used:
             # batched path: the dominant kernel is the tcgen05 emit pass; algorithmic flops = 2 nq N d
             p2_ms = base.get_option("stat_gemm_pass2_us") / 1e3

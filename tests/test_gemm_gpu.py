@@ -82,8 +82,13 @@ def test_small_batches_do_not_use_gemm(b200):
     db, q = oracle.synth_rows(70_000, 128, 1), oracle.synth_rows(8, 128, 2)
     idx = b200.IndexFlat(128, 0)
     idx.add(db)
-    idx.search(q, 5)
-    assert idx.get_option("stat_gemm_used") == 0
+    idx.search(q[:3], 5)
+    assert idx.get_option("stat_gemm_used") == 0  # below gemm_min_nq (4)
+    D, I = idx.search(q, 5)
+    assert idx.get_option("stat_gemm_used") == 1  # measured crossover: 8 queries already favour the tensor cores 5x
+    Dw, Iw = oracle.search(0, db, q, 5, order=oracle.ORDER_DEVICE)
+    np.testing.assert_array_equal(I, Iw)
+    np.testing.assert_array_equal(D, Dw)
 
 
 @pytest.mark.parametrize("n,d,nq,k,normalize", [(120_000, 384, 100, 10, True), (200_000, 768, 130, 100, False),
