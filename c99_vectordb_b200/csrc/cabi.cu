@@ -85,12 +85,13 @@ struct b200_index {
     int64_t opt_gemm_min_nq = 4, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2;
     // read-only statistics of the last batched (K3) search
     int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
-            stat_gemm_pass2_us = 0, stat_gemm_rerank_us = 0;
+            stat_gemm_pass2_us = 0, stat_gemm_rerank_us = 0, stat_gemm_scan_fallbacks = 0;
     // K3 state
     __nv_bfloat16* sh_rows = nullptr;  // bf16 shadow of the rows [ntotal, kpad]
     float* sh_norm2 = nullptr;
     unsigned int* sh_maxnorm = nullptr;
     int64_t sh_valid_rows = -1;        // rows covered by the shadow (-1 = none)
+    int64_t sh_failed_rows = -1;       // ntotal at which the shadow allocation last failed (no retry until it changes)
     size_t sh_cap_rows = 0;
     __nv_bfloat16* g_qb = nullptr;     // bf16 queries [m_tiles*128, kpad]
     float* g_qnorm2 = nullptr;
@@ -290,6 +291,7 @@ static const OptName kOpts[] = {
     {"gemm_cta_group", &b200_index::opt_gemm_cta_group},
     {"stat_gemm_used", &b200_index::stat_gemm_used},
     {"stat_gemm_fallbacks", &b200_index::stat_gemm_fallbacks},
+    {"stat_gemm_scan_fallbacks", &b200_index::stat_gemm_scan_fallbacks},
     {"stat_gemm_cand_total", &b200_index::stat_gemm_cand_total},
     {"stat_gemm_pass1_us", &b200_index::stat_gemm_pass1_us},
     {"stat_gemm_pass2_us", &b200_index::stat_gemm_pass2_us},
@@ -832,12 +834,16 @@ static int ensure_shadow(b200_index* ix, cudaStream_t st) {
         ix->sh_cap_rows = 0;
         size_t cap = (size_t)std::max<int64_t>(ix->ntotal, ix->capacity);
         cudaError_t e = cudaMalloc((void**)&ix->sh_rows, cap * kpad * sizeof(__nv_bfloat16));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&ix->sh_norm2, cap * sizeof(float));
         if (e != cudaSuccess) {
+            // not an error for the search: the caller falls back to the exact scan (status 2)
             cudaGetLastError();
-            return fail("cannot allocate the %.2f GB bf16 shadow for batched search: %s", (double)cap * kpad * 2 / 1e9,
-                        cudaGetErrorString(e));
+            if (ix->sh_rows) cudaFree(ix->sh_rows);
+            ix->sh_rows = nullptr;
+            ix->sh_failed_rows = ix->ntotal;
+            fail("no room for the %.2f GB bf16 shadow: %s", (double)cap * kpad * 2 / 1e9, cudaGetErrorString(e));
+            return 2;
         }
-        CK(cudaMalloc((void**)&ix->sh_norm2, cap * sizeof(float)));
         ix->sh_cap_rows = cap;
     }
     if (!ix->sh_maxnorm) CK(cudaMalloc((void**)&ix->sh_maxnorm, sizeof(unsigned int)));
@@ -855,14 +861,14 @@ static int search_scan_block(b200_index* ix, const float* q_dev, int64_t nq, int
                              cudaStream_t st);
 
 static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev, int64_t* I_dev,
-                       cudaStream_t st) {
+                       cudaStream_t st, int depth = 0) {
     const int kpad = gemm_kpad(ix);
     const uint64_t n = (uint64_t)ix->ntotal;
     const uint32_t NT = (uint32_t)((n + G3_BLOCK_N - 1) / G3_BLOCK_N);
     const uint32_t m_tiles = (uint32_t)((nq + G3_BLOCK_M - 1) / G3_BLOCK_M);
     const uint32_t cap = 4096;
     const int cg = ix->opt_gemm_cta_group == 1 ? 1 : 2;
-    CKI(ensure_shadow(ix, st));
+    CKI(ensure_shadow(ix, st));  // 2 = no memory for the shadow: the caller uses the scan path
     // ---- scratch ----
     const size_t qb_elems = (size_t)((m_tiles + 1) / 2 * 2) * G3_BLOCK_M * kpad;  // whole 256-query groups
     // sampled tiles: each contributes 8 group maxima; at most 8192 maxima per query are sorted
@@ -956,12 +962,12 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
         // is kept below G/8 so that two of the top scores rarely share a group.
         const uint32_t G = T * 8;
         double sample_rows = (double)T * G3_BLOCK_N;
-        double want = (double)std::max<int64_t>(ix->opt_gemm_emit_factor, 2) * (double)k;
+        // a retry of uncertified queries (depth 1) widens the net 3x
+        double want = (double)std::max<int64_t>(ix->opt_gemm_emit_factor, 2) * (depth ? 3.0 : 1.0) * (double)k;
+        want = std::min(want, 0.7 * cap);
         double r = want * std::min(1.0, sample_rows / (double)n);
         uint32_t rank = (uint32_t)std::min<double>(std::max(r, 8.0), (double)(G / 8));
-        uint32_t m = 2;
-        while (m < G) m <<= 1;
-        select_theta_kernel<<<(unsigned)nq, 256, (size_t)m * 4, st>>>(ix->g_tilemax, G, rank, ix->g_theta);
+        select_theta_kernel<<<(unsigned)nq, 256, 0, st>>>(ix->g_tilemax, G, rank, ix->g_theta);
         ++ix->launches;
         CK(cudaGetLastError());
     }
@@ -1025,9 +1031,14 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
         cand_total += counts[(size_t)i];
         if (!cert[(size_t)i]) bad.push_back(i);
     }
-    ix->stat_gemm_used = 1;
-    ix->stat_gemm_fallbacks = (int64_t)bad.size();
-    ix->stat_gemm_cand_total = cand_total;
+    if (depth == 0) {
+        ix->stat_gemm_used = 1;
+        ix->stat_gemm_fallbacks = (int64_t)bad.size();
+        ix->stat_gemm_cand_total = cand_total;
+        ix->stat_gemm_scan_fallbacks = 0;
+    } else {
+        ix->stat_gemm_scan_fallbacks = (int64_t)bad.size();
+    }
     if (!bad.empty()) {
         // gather the failed queries, search them exactly 8 at a time, scatter the results back
         const size_t nb = bad.size();
@@ -1037,7 +1048,16 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
         CK(cudaMalloc((void**)&Itmp, nb * (size_t)k * 8));
         for (size_t j = 0; j < nb; ++j)
             CK(cudaMemcpyAsync(qtmp + j * ix->d, q_dev + (size_t)bad[j] * ix->d, (size_t)ix->d * 4, cudaMemcpyDeviceToDevice, st));
-        int rc = search_scan_block(ix, qtmp, (int64_t)nb, k, Dtmp, Itmp, st);
+        // first retry on the tensor cores with a 3x wider threshold (one more sweep of the shadow serves
+        // up to 256 stragglers; the scan kernel needs a pass per 8), then the exact scan for what is left
+        const int64_t s_p1 = ix->stat_gemm_pass1_us, s_p2 = ix->stat_gemm_pass2_us, s_rr = ix->stat_gemm_rerank_us;
+        int rc = depth == 0 ? search_gemm(ix, qtmp, (int64_t)nb, k, Dtmp, Itmp, st, 1)
+                            : search_scan_block(ix, qtmp, (int64_t)nb, k, Dtmp, Itmp, st);
+        if (depth == 0) {
+            ix->stat_gemm_pass1_us = s_p1;
+            ix->stat_gemm_pass2_us = s_p2;
+            ix->stat_gemm_rerank_us = s_rr;
+        }
         if (rc == 0)
             for (size_t j = 0; j < nb; ++j) {
                 cudaMemcpyAsync(D_dev + (size_t)bad[j] * k, Dtmp + j * k, (size_t)k * 4, cudaMemcpyDeviceToDevice, st);
@@ -1099,13 +1119,15 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
     const bool fullrank = k >= ix->opt_fullrank_min_k || k > B200_FUSED_K_MAX;
     ix->stat_gemm_used = 0;
     if (!fullrank) {
-        if (!ix->cur_mask && !ix->xchg_active && gemm_eligible(ix, nq, k)) {
+        if (!ix->cur_mask && !ix->xchg_active && gemm_eligible(ix, nq, k) && ix->sh_failed_rows != ix->ntotal) {
             // K3 in blocks of at most 16384 queries (bounds the candidate scratch)
-            for (int64_t q0 = 0; q0 < nq; q0 += 16384) {
+            int rc = 0;
+            for (int64_t q0 = 0; q0 < nq && rc == 0; q0 += 16384) {
                 int64_t nb = std::min<int64_t>(16384, nq - q0);
-                CKI(search_gemm(ix, q_dev + (size_t)q0 * ix->d, nb, k, D_dev + (size_t)q0 * k, I_dev + (size_t)q0 * k, st));
+                rc = search_gemm(ix, q_dev + (size_t)q0 * ix->d, nb, k, D_dev + (size_t)q0 * k, I_dev + (size_t)q0 * k, st);
             }
-            return 0;
+            if (rc != 2) return rc;
+            ix->stat_gemm_used = 0;  // no memory for the bf16 shadow: exact scan instead
         }
         return search_scan_block(ix, q_dev, nq, k, D_dev, I_dev, st);
     }

@@ -437,30 +437,43 @@ shadow_rows_kernel(const uint8_t* __restrict__ rows, uint64_t pitch, int store, 
     if (lane == 0 && max_norm2_bits) atomicMax(max_norm2_bits, __float_as_uint(wmax));  // non-negative floats order as uints
 }
 
-// ---- threshold selection: theta[q] = rank-th largest of tilemax[q, 0..T) ------------------------------
+// ---- threshold selection: theta[q] ~ rank-th largest of tilemax[q, 0..T) ----------------------------
+// Two-level radix select on the monotone integer image of the scores: a 256-bin histogram of the top
+// byte locates the bin holding the rank-th largest value, a second histogram of the next byte inside
+// that bin refines it; theta is the LOWER edge of the selected sub-bin, i.e. never above the true
+// rank-th value (a slightly lower threshold only emits a few more candidates).  One CTA per query.
 __global__ void __launch_bounds__(256)
 select_theta_kernel(const float* __restrict__ tilemax, uint32_t T, uint32_t rank, float* __restrict__ theta) {
-    extern __shared__ __align__(16) uint8_t sm[];
-    float* a = reinterpret_cast<float*>(sm);
-    uint32_t m = 2;
-    while (m < T) m <<= 1;
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t sel_bin, sel_rank;
     const float* src = tilemax + (size_t)blockIdx.x * T;
-    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) a[i] = i < T ? src[i] : -INFINITY;
-    for (uint32_t size = 2; size <= m; size <<= 1)
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            __syncthreads();
-            for (uint32_t t = threadIdx.x; t < (m >> 1); t += blockDim.x) {
-                uint32_t lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
-                bool desc = ((lo & size) == 0);
-                float x = a[lo], y = a[hi];
-                if (desc ? (x < y) : (x > y)) {
-                    a[lo] = y;
-                    a[hi] = x;
-                }
-            }
+    uint32_t prefix = 0, want = rank < T ? rank : T - 1;  // 0-based rank among values sorted descending
+    for (int level = 0; level < 2; ++level) {
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        const int shift = 24 - 8 * level;
+        for (uint32_t i = threadIdx.x; i < T; i += blockDim.x) {
+            uint32_t o = b200_ord_f32(src[i]);
+            if (level == 0 || (o >> 24) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
         }
-    __syncthreads();
-    if (threadIdx.x == 0) theta[blockIdx.x] = a[rank < T ? rank : T - 1];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            int b = 255;
+            for (; b > 0; --b) {  // walk from the largest values down
+                if (acc + hist[b] > want) break;
+                acc += hist[b];
+            }
+            sel_bin = (uint32_t)b;
+            sel_rank = want - acc;
+        }
+        __syncthreads();
+        if (level == 0) prefix = sel_bin;
+        else prefix = (prefix << 8) | sel_bin;
+        want = sel_rank;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) theta[blockIdx.x] = b200_unord_f32(prefix << 16);  // lower edge of the 16-bit prefix bucket
 }
 
 // ---- exact re-rank + certificate -------------------------------------------------------------------
