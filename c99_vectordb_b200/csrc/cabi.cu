@@ -587,45 +587,52 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
     const int kk = fullrank ? 1 : k;
     const size_t budget = ix->smem_optin - 1024;
     int variant = (int)ix->opt_variant;
-    // AUTO (measured, profiles/README.md): fp32 rows -> the TMA-staged ring with dynamic tiles
-    // (10M x 768: 7.48 TB/s, 40M x 384: 7.41 TB/s); bf16 rows carry 2.5x the instructions per byte and
-    // want the 32 resident warps/SM of the direct-load variant with static tiles (6.42 vs 5.37 TB/s).
-    if (variant == B200_SCAN_AUTO) variant = (ix->store == B200_STORE_F32) ? B200_VARIANT_BULK : B200_VARIANT_LDG;
+    // AUTO (measured, profiles/README.md r1_sweep8_*): fp32 rows of >= 1.5 KB -> the TMA-staged ring
+    // with dynamic tiles as long as >= 5 warps x 2 stages fit (d = 384..1024: 1.05-1.14 of the
+    // measured peak vs 1.03-1.05 for direct loads); short rows (per-row overhead dominates), very
+    // long rows (the per-warp rings no longer fit) and bf16 rows (2.5x the instructions per byte)
+    // -> direct loads with 32 resident warps/SM (0.97-1.06).
+    const bool auto_variant = variant == B200_SCAN_AUTO;
+    if (auto_variant) variant = (ix->store == B200_STORE_F32 && ix->pitch >= 1536) ? B200_VARIANT_BULK : B200_VARIANT_LDG;
     if (variant == B200_VARIANT_BULK) {
         int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_MAX / 32);
+        const int nw_min = auto_variant ? 5 : 1;
         bool ok = false;
-        for (; nw >= 1; nw >>= 1) {
-            uint32_t tr;
+        // Every warp owns `stages` tiles of tile_rows rows.  Prefer ~12 KB tiles, but shrink the tile
+        // (down to one RB-row group) before giving up warps: 8 warps x 2 stages is what keeps the
+        // ring fed.  Longer rows drop warps one at a time (7 warps at d = 896 and 6 at d = 1024 still
+        // measure 1.12-1.13); below 5 warps AUTO uses the direct-load variant instead.
+        for (; nw >= nw_min && !ok; --nw) {
+            uint32_t m_pref;
             if (ix->opt_tile_rows > 0)
-                tr = (uint32_t)((ix->opt_tile_rows + SCAN_RB - 1) / SCAN_RB * SCAN_RB);
-            else {
-                double groups = 12288.0 / ((double)SCAN_RB * ix->pitch);
-                uint32_t m = (uint32_t)std::max(1.0, groups + 0.5);
-                tr = m * SCAN_RB;
+                m_pref = (uint32_t)((ix->opt_tile_rows + SCAN_RB - 1) / SCAN_RB);
+            else
+                m_pref = (uint32_t)std::max(1.0, 12288.0 / ((double)SCAN_RB * ix->pitch) + 0.5);
+            for (uint32_t m = m_pref; m >= 1 && !ok; --m) {
+                uint32_t tr = m * SCAN_RB;
+                uint64_t tile_bytes = (uint64_t)tr * ix->pitch;
+                if (tile_bytes > (1u << 19)) continue;  // mbarrier tx-count headroom
+                uint32_t scratch = std::max<uint32_t>(B200_FINAL_BUF_KEYS, next_pow2((uint32_t)(nw * kk)));
+                size_t fixed = scan_smem_bytes(B200_VARIANT_BULK, nw, qb, qstride, kk, fullrank, 0, 0, scratch);
+                // ring replaces the scratch region when larger
+                size_t fixed_wo_scratch = fixed - (((size_t)scratch * 8 + 127) & ~(size_t)127);
+                if (fixed_wo_scratch + 64 >= budget) continue;
+                size_t avail = budget - fixed_wo_scratch - 64;
+                uint32_t stages = (uint32_t)std::min<uint64_t>(8, avail / ((uint64_t)nw * tile_bytes + (uint64_t)nw * 12));
+                if (ix->opt_stages > 0) stages = std::min<uint32_t>(stages, (uint32_t)ix->opt_stages);
+                if (stages < 2) continue;
+                size_t smem = scan_smem_bytes(B200_VARIANT_BULK, nw, qb, qstride, kk, fullrank, stages, (uint32_t)tile_bytes, scratch);
+                if (smem > budget) continue;
+                pl.variant = B200_VARIANT_BULK;
+                pl.nw = nw;
+                pl.tile_rows = tr;
+                pl.stages = stages;
+                pl.tile_bytes = (uint32_t)tile_bytes;
+                pl.scratch_keys = scratch;
+                pl.smem = smem;
+                pl.grid = ix->num_sms;  // one persistent CTA per SM
+                ok = true;
             }
-            uint64_t tile_bytes = (uint64_t)tr * ix->pitch;
-            if (tile_bytes > (1u << 19)) break;  // mbarrier tx-count headroom
-            uint32_t scratch = std::max<uint32_t>(B200_FINAL_BUF_KEYS, next_pow2((uint32_t)(nw * kk)));
-            size_t fixed = scan_smem_bytes(B200_VARIANT_BULK, nw, qb, qstride, kk, fullrank, 0, 0, scratch);
-            // ring replaces the scratch region when larger
-            size_t fixed_wo_scratch = fixed - (((size_t)scratch * 8 + 127) & ~(size_t)127);
-            if (fixed_wo_scratch + 64 >= budget) continue;
-            size_t avail = budget - fixed_wo_scratch - 64;
-            uint32_t stages = (uint32_t)std::min<uint64_t>(8, avail / ((uint64_t)nw * tile_bytes + (uint64_t)nw * 12));
-            if (ix->opt_stages > 0) stages = std::min<uint32_t>(stages, (uint32_t)ix->opt_stages);
-            if (stages < 2) continue;
-            size_t smem = scan_smem_bytes(B200_VARIANT_BULK, nw, qb, qstride, kk, fullrank, stages, (uint32_t)tile_bytes, scratch);
-            if (smem > budget) continue;
-            pl.variant = B200_VARIANT_BULK;
-            pl.nw = nw;
-            pl.tile_rows = tr;
-            pl.stages = stages;
-            pl.tile_bytes = (uint32_t)tile_bytes;
-            pl.scratch_keys = scratch;
-            pl.smem = smem;
-            pl.grid = ix->num_sms;  // one persistent CTA per SM
-            ok = true;
-            break;
         }
         if (!ok) variant = B200_VARIANT_LDG;
     }

@@ -62,7 +62,7 @@ def main():
     out = open(a.out, "a")
     configs = []
     if a.quick:
-        configs += [dict(scan_variant=1), dict(scan_variant=2)]
+        configs += [dict(scan_variant=0), dict(scan_variant=1), dict(scan_variant=2)]
     else:
         for dyn, ef, tr in itertools.product((1, 0), (0, 1), (0, 8)):
             configs.append(dict(scan_variant=1, scan_tile_rows=tr, scan_l2_evict_first=ef, scan_dynamic_tiles=dyn))
