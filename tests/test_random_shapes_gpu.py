@@ -7,7 +7,9 @@ from oracle import oracle
 
 pytestmark = pytest.mark.gpu
 
-CASES = 48
+import os
+
+CASES = int(os.environ.get("B200_RANDOM_CASES", "48"))
 
 
 @pytest.fixture(scope="module")
