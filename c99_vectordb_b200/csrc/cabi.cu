@@ -82,7 +82,7 @@ struct b200_index {
     int64_t opt_variant = B200_SCAN_AUTO, opt_warps = 8, opt_stages = 0, opt_tile_rows = 0,
             opt_ctas_per_sm = 0, opt_evict_first = 0, opt_fullrank_min_k = B200_FUSED_K_MAX + 1,
             opt_normalize_queries = 0, opt_qb = 0, opt_dynamic = -1, opt_claim_chunk = 0, opt_fused_tail = -1;
-    int64_t opt_gemm_min_nq = 4, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2;
+    int64_t opt_gemm_min_rows = 4096, opt_gemm_min_nq = 4, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2;
     // read-only statistics of the last batched (K3) search
     int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
             stat_gemm_pass2_us = 0, stat_gemm_rerank_us = 0, stat_gemm_scan_fallbacks = 0;
@@ -285,6 +285,7 @@ static const OptName kOpts[] = {
     {"scan_claim_chunk", &b200_index::opt_claim_chunk},
     {"scan_fused_tail", &b200_index::opt_fused_tail},
     {"gemm_min_nq", &b200_index::opt_gemm_min_nq},
+    {"gemm_min_rows", &b200_index::opt_gemm_min_rows},
     {"gemm_emit_factor", &b200_index::opt_gemm_emit_factor},
     {"gemm_chunk_tiles", &b200_index::opt_gemm_chunk_tiles},
     {"gemm_sample_tiles", &b200_index::opt_gemm_sample_tiles},
@@ -820,7 +821,7 @@ static int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uin
 
 static bool gemm_eligible(b200_index* ix, int64_t nq, int64_t k) {
     return ix->opt_gemm_min_nq > 0 && nq >= ix->opt_gemm_min_nq && k <= B200_FUSED_K_MAX &&
-           ix->ntotal >= 65536 && ix->ntotal >= 1024 * k && ix->d >= 32 && k < ix->opt_fullrank_min_k;
+           ix->ntotal >= ix->opt_gemm_min_rows && ix->ntotal >= 512 * k && ix->d >= 32 && k < ix->opt_fullrank_min_k;
 }
 
 // K of the shadow GEMM: d (+2 columns carrying |y|^2/2 and -1 for L2), padded to whole 64-column blocks

@@ -56,7 +56,7 @@ def test_batched_ip_exact(b200, n, d, nq, k):
 
 
 def test_too_few_rows_for_k_stays_on_the_scan_path(b200):
-    st = run_case(b200, 66000, 1024, 33, 256)  # n < 1024 k: the threshold statistic cannot resolve k
+    st = run_case(b200, 66000, 1024, 33, 256)  # n < 512 k: the threshold statistic cannot resolve k
     assert st["stat_gemm_used"] == 0
 
 
@@ -103,3 +103,11 @@ def test_batched_l2_exact(b200, n, d, nq, k, normalize):
 def test_batched_l2_bf16_store(b200):
     st = run_case(b200, 100_000, 512, 80, 10, metric=1, store="bf16")
     assert st["stat_gemm_used"] == 1
+
+
+@pytest.mark.parametrize("n,d,nq,k,metric", [(10_000, 384, 100, 10, 0), (5_200, 384, 37, 10, 1), (4_096, 64, 40, 5, 0), (20_000, 768, 50, 30, 1)])
+def test_small_databases_use_the_tensor_path_too(b200, n, d, nq, k, metric):
+    """BASELINE config 0 shape (10k x 384, 100 queries, k=10): one K3 sweep instead of 13 scan passes."""
+    st = run_case(b200, n, d, nq, k, metric=metric, normalize=True)
+    assert st["stat_gemm_used"] == 1
+    assert st["stat_gemm_fallbacks"] <= max(2, nq // 4), st

@@ -10,11 +10,15 @@ n, d, nq, k = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv
 idx = m.IndexFlat(d, 0)
 idx.set_option("gemm_min_nq", 32)
 if len(sys.argv) > 5: idx.set_option("gemm_cta_group", int(sys.argv[5]))
+if len(sys.argv) > 6: idx.set_option("gemm_min_rows", int(sys.argv[6]))
 idx.add_synthetic(n, 1234)
 q = oracle.synth_rows(nq, d, 5678)
 t0 = time.time(); D, I = idx.search(q, k); t1 = time.time()
 print("first search s", round(t1 - t0, 3), {s: idx.get_option(s) for s in ("stat_gemm_used", "stat_gemm_fallbacks", "stat_gemm_cand_total", "stat_gemm_pass1_us", "stat_gemm_pass2_us", "stat_gemm_rerank_us")}, flush=True)
-t0 = time.time(); D, I = idx.search(q, k); t1 = time.time()
+ts=[]
+for _ in range(20):
+    t0 = time.time(); D, I = idx.search(q, k); ts.append(time.time()-t0)
+t0=0; t1=sorted(ts)[10]
 print("second search s", round(t1 - t0, 3), {s: idx.get_option(s) for s in ("stat_gemm_fallbacks", "stat_gemm_cand_total", "stat_gemm_pass1_us", "stat_gemm_pass2_us", "stat_gemm_rerank_us")}, flush=True)
 if n <= 2_000_000:
     db = oracle.synth_rows(n, d, 1234)
