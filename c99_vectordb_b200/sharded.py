@@ -134,11 +134,12 @@ class ShardedIndexFlat:
         return True
 
     def _fused_ok(self, nq: int, k: int) -> bool:
-        # The fused exchange lives in the scan kernel's tail: one launch per block of <= 8 queries.
-        # Larger batches go through NCCL so that every shard can use the tensor-core path (K3).
-        # Every rank must hold rows (an empty shard launches no kernel and nobody would flag for it).
+        # The fused exchange lives in the scan kernel's tail and serves single queries (the latency
+        # path).  Batches go through NCCL so that every shard can use the tensor-core path (K3), which
+        # beats the scan from 2 queries on.  Every rank must hold rows (an empty shard launches no
+        # kernel and nobody would flag for it).
         lo, hi = shard_range(self.ntotal_global, self.world, self.world - 1)
-        return self._fused and nq <= 8 and k <= 256 and hi > lo
+        return self._fused and nq == 1 and k <= 256 and hi > lo
 
     # ---- search -----------------------------------------------------------------------------
     def _buffers(self, nq: int, k: int):

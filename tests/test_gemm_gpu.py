@@ -82,8 +82,8 @@ def test_small_batches_do_not_use_gemm(b200):
     db, q = oracle.synth_rows(70_000, 128, 1), oracle.synth_rows(8, 128, 2)
     idx = b200.IndexFlat(128, 0)
     idx.add(db)
-    idx.search(q[:3], 5)
-    assert idx.get_option("stat_gemm_used") == 0  # below gemm_min_nq (4)
+    idx.search(q[:1], 5)
+    assert idx.get_option("stat_gemm_used") == 0  # single queries stay on the fp32 scan (gemm_min_nq = 2)
     D, I = idx.search(q, 5)
     assert idx.get_option("stat_gemm_used") == 1  # measured crossover: 8 queries already favour the tensor cores 5x
     Dw, Iw = oracle.search(0, db, q, 5, order=oracle.ORDER_DEVICE)

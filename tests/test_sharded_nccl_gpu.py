@@ -56,9 +56,21 @@ def _worker(rank, world, port, out_dir):
         np.testing.assert_array_equal(D, Dw)
         # fused exchange: the scan kernel stores into the peers' buffers over NVLink and merges itself
         assert idx.enable_fused_exchange()
-        for nq, k in ((1, 10), (3, 10), (8, 100), (11, 7)):
+        for nq, k in ((1, 10), (1, 100), (3, 10), (8, 100), (11, 7)):
             q = oracle.synth_rows(nq, 384, 999 + nq)
             Df, If = idx.search(q, k)
+            if nq > 1:  # the fused kernel itself also handles query blocks (forced through the C ABI)
+                import ctypes as C
+                import torch
+                from c99_vectordb_b200 import _cabi
+                qt = torch.from_numpy(q).cuda()
+                Dt = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+                It = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+                _cabi.check(_cabi.load().b200_index_search_exchange_dev(idx.local.index._h, qt.data_ptr(), nq, k, Dt.data_ptr(),
+                                                                        It.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream or 1)))
+                torch.cuda.synchronize()
+                np.testing.assert_array_equal(It.cpu().numpy(), If)
+                np.testing.assert_array_equal(Dt.cpu().numpy(), Df)
             Dw, Iw = oracle.search(1, oracle.synth_rows(300_000, 384, 1234), q, k, order=oracle.ORDER_DEVICE)
             np.testing.assert_array_equal(If, Iw)
             np.testing.assert_array_equal(Df, Dw)
@@ -70,9 +82,11 @@ def _worker(rank, world, port, out_dir):
         Dw2, Iw2 = oracle.search(1, oracle.synth_rows(300_000, 384, 1234), qb, 10, order=oracle.ORDER_DEVICE)
         np.testing.assert_array_equal(Ib, Iw2)
         np.testing.assert_array_equal(Db, Dw2)
-        for rep in range(20):  # back-to-back searches exercise the double-buffered slots
-            Df2, If2 = idx.search(q, k)
-            np.testing.assert_array_equal(If2, Iw)
+        q1 = oracle.synth_rows(1, 384, 31337)
+        Dw1, Iw1 = oracle.search(1, oracle.synth_rows(300_000, 384, 1234), q1, 10, order=oracle.ORDER_DEVICE)
+        for rep in range(20):  # back-to-back fused searches exercise the double-buffered slots
+            Df2, If2 = idx.search(q1, 10)
+            np.testing.assert_array_equal(If2, Iw1)
         np.save(os.path.join(out_dir, f"ok_{rank}.npy"), I)
     finally:
         dist.destroy_process_group()
