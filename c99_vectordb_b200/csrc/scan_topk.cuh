@@ -1,8 +1,9 @@
-// scan_topk.cuh — K2: the single / small-batch query GEMV scan with a fused top-k.
+// scan_topk.cuh — K2: the single-query GEMV scan with a fused top-k (query blocks of up to 8 for
+// the cases the tensor-core path does not take: masks, tiny databases, its certificate fallback).
 //
-// Replaces index.search(x[nq,d], k) for nq < ~20 (memo_cli.py:292 -> faiss IndexFlat::search,
-// "seq" path [upstream]).  HBM-bound: every database row is read exactly once per launch,
-// nothing but the final [nq,k] result is written.
+// Replaces index.search(x[1,d], k) (memo_cli.py:292 -> faiss IndexFlat::search, "seq" path
+// [upstream]).  HBM-bound: every database row is read exactly once per launch, nothing but the
+// final [nq,k] result is written.
 //
 //   VARIANT_BULK : every warp owns a private ring of shared-memory stages that it fills itself
 //                  with 1-D cp.async.bulk (TMA engine, SASS UBLKCP) and consumes with 128-bit
@@ -20,7 +21,9 @@
 // warm-up: ~k*ln(rows_per_warp/k) inserts per warp per scan).  At the end of the scan the CTA
 // bitonic-sorts its warps' lists, writes its best k keys, and the LAST CTA to finish (atomic
 // ticket) merges all CTA partials, translates row -> record id (K5) and writes D/I — so a search
-// is a single launch.
+// is a single launch.  On a sharded index the same tail also exchanges the result with the peer
+// GPUs over NVLink and merges (exchange_and_merge).  Tiles are claimed in ascending runs from a
+// global counter (dynamic scheduler) unless p.dynamic == 0.
 #pragma once
 #include "common.cuh"
 

@@ -40,7 +40,7 @@ extern "C" {
 #define B200_STORE_F32 0
 #define B200_STORE_BF16 1
 
-/* search path selection (b200_index_set_option "scan_variant") */
+/* scan kernel selection (b200_index_set_option "scan_variant") */
 #define B200_SCAN_AUTO 0
 #define B200_SCAN_BULK 1 /* cp.async.bulk (TMA) staged smem ring */
 #define B200_SCAN_LDG 2  /* direct 128-bit ld.global.nc */
@@ -64,9 +64,17 @@ int b200_index_destroy(b200_index* ix);
 int b200_index_reset(b200_index* ix);
 /* make room for n_total rows without reallocation */
 int b200_index_reserve(b200_index* ix, int64_t n_total);
-/* named integer options: "scan_variant", "scan_warps", "scan_stages", "scan_tile_rows",
- * "scan_ctas_per_sm", "scan_l2_evict_first", "fullrank_min_k" — tuning knobs for the sweep
- * harness; defaults are the measured best. */
+/* Named integer options (tuning knobs for the sweep harness; defaults are the measured best):
+ *   scan_variant          0 auto | 1 TMA-staged ring | 2 direct 128-bit loads
+ *   scan_warps, scan_stages, scan_tile_rows, scan_ctas_per_sm, scan_l2_evict_first,
+ *   scan_query_block (1|2|4|8), scan_dynamic_tiles (-1 auto|0|1), scan_claim_chunk, scan_fused_tail
+ *   fullrank_min_k        k at or above which the full-ranking (radix sort) path is used (default 257)
+ *   normalize_queries     1: L2-normalise queries on the device before searching (cosine)
+ *   gemm_min_nq           batched tensor-core path (K3) for nq >= this (default 2; 0 disables)
+ *   gemm_min_rows, gemm_emit_factor, gemm_sample_tiles, gemm_chunk_tiles, gemm_cta_group (1|2)
+ * Read-only statistics of the last search (b200_index_get_option): stat_gemm_used,
+ *   stat_gemm_fallbacks (queries retried), stat_gemm_scan_fallbacks (queries recomputed by the scan),
+ *   stat_gemm_cand_total, stat_gemm_pass1_us, stat_gemm_pass2_us, stat_gemm_rerank_us. */
 int b200_index_set_option(b200_index* ix, const char* name, int64_t value);
 int b200_index_get_option(b200_index* ix, const char* name, int64_t* out_value);
 
@@ -91,7 +99,9 @@ int b200_index_add_synthetic(b200_index* ix, int64_t n, uint64_t seed, int64_t f
  *           (IndexIDMap2::search over IndexFlatIP/IndexFlatL2 [upstream]).
  * D is float32 [nq,k], I is int64 [nq,k], best-first, padded with id -1 and
  * -FLT_MAX (IP) / +FLT_MAX (L2).  Any k >= 1 is accepted (memo asks for k = ntotal,
- * memo_cli.py:291). */
+ * memo_cli.py:291).  Results are exact on every path: single queries use the HBM-bound scan kernel,
+ * batches the tcgen05 tensor-core path with an exact fp32 re-rank and a certificate (uncertified
+ * queries are recomputed by the scan), k > 256 the full-ranking radix sort. */
 int b200_index_search(b200_index* ix, const float* q_host, int64_t nq, int64_t k, float* D_host,
                       int64_t* I_host);
 /* device-resident variant: q, D, I are device pointers; work is enqueued on `stream`
