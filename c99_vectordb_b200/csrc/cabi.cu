@@ -79,7 +79,7 @@ struct b200_index {
     uint32_t* fr_hist = nullptr;
     size_t fr_cap = 0, fr_hi_cap = 0, fr_hist_cap = 0;
     // options
-    int64_t opt_variant = B200_SCAN_AUTO, opt_warps = 8, opt_stages = 0, opt_tile_rows = 0,
+    int64_t opt_variant = B200_SCAN_AUTO, opt_warps = 16, opt_stages = 0, opt_tile_rows = 0,
             opt_ctas_per_sm = 0, opt_evict_first = 0, opt_fullrank_min_k = B200_FUSED_K_MAX + 1,
             opt_normalize_queries = 0, opt_qb = 0, opt_dynamic = -1, opt_claim_chunk = 0, opt_fused_tail = -1;
     int64_t opt_gemm_min_rows = 4096, opt_gemm_min_nq = 2, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2;
@@ -588,21 +588,22 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
     const int kk = fullrank ? 1 : k;
     const size_t budget = ix->smem_optin - 1024;
     int variant = (int)ix->opt_variant;
-    // AUTO (measured, profiles/README.md r1_sweep8_*): fp32 rows of >= 1.5 KB -> the TMA-staged ring
-    // with dynamic tiles as long as >= 5 warps x 2 stages fit (d = 384..1024: 1.05-1.14 of the
-    // measured peak vs 1.03-1.05 for direct loads); short rows (per-row overhead dominates), very
-    // long rows (the per-warp rings no longer fit) and bf16 rows (2.5x the instructions per byte)
-    // -> direct loads with 32 resident warps/SM (0.97-1.06).
+    // AUTO (measured over d = 64..2048, fp32 and bf16: profiles/README.md, r1_sweep11_*): the
+    // TMA-staged ring with dynamic tiles and as many warps as fit (<= 16) x 2 stages.  Short rows and
+    // bf16 rows carry more instructions per byte and want the extra warps (bf16 d=1024: 1.09-1.12 of
+    // the measured peak vs 1.02 for direct loads); long rows still win with 3-4 warps (d=2048: 1.12
+    // vs 1.03).  Rows under 768 bytes (fewer than 48 16-byte chunks: lanes idle in both variants,
+    // 0.5-0.9) go to the direct-load variant with its 32 resident warps/SM.
     const bool auto_variant = variant == B200_SCAN_AUTO;
-    if (auto_variant) variant = (ix->store == B200_STORE_F32 && ix->pitch >= 1536) ? B200_VARIANT_BULK : B200_VARIANT_LDG;
+    if (auto_variant) variant = ix->pitch >= 768 ? B200_VARIANT_BULK : B200_VARIANT_LDG;
     if (variant == B200_VARIANT_BULK) {
-        int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_MAX / 32);
-        const int nw_min = auto_variant ? 5 : 1;
+        int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_BULK / 32);
+        const int nw_min = auto_variant ? 3 : 1;
         bool ok = false;
         // Every warp owns `stages` tiles of tile_rows rows.  Prefer ~12 KB tiles, but shrink the tile
         // (down to one RB-row group) before giving up warps: 8 warps x 2 stages is what keeps the
-        // ring fed.  Longer rows drop warps one at a time (7 warps at d = 896 and 6 at d = 1024 still
-        // measure 1.12-1.13); below 5 warps AUTO uses the direct-load variant instead.
+        // ring fed.  Longer rows drop warps one at a time (7 warps at d = 896, 6 at d = 1024, 3 at
+        // d = 2048 still measure 1.12-1.13); below 3 warps AUTO uses the direct-load variant instead.
         for (; nw >= nw_min && !ok; --nw) {
             uint32_t m_pref;
             if (ix->opt_tile_rows > 0)
@@ -638,7 +639,7 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
         if (!ok) variant = B200_VARIANT_LDG;
     }
     if (variant == B200_VARIANT_LDG) {
-        int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_MAX / 32);
+        int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_LDG / 32);
         for (;; nw >>= 1) {
             if (nw < 1) return fail("k=%d does not fit the fused top-k shared-memory budget", k);
             uint32_t scratch = std::max<uint32_t>(B200_FINAL_BUF_KEYS, next_pow2((uint32_t)(nw * kk)));

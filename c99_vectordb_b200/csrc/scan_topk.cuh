@@ -30,7 +30,8 @@
 #define B200_VARIANT_BULK 1
 #define B200_VARIANT_LDG 2
 
-#define B200_SCAN_THREADS_MAX 256
+#define B200_SCAN_THREADS_BULK 512  // ring variant: one persistent CTA per SM, up to 16 warps
+#define B200_SCAN_THREADS_LDG 256   // direct-load variant: 4 CTAs of 8 warps per SM (<= 64 registers)
 #define B200_FUSED_K_MAX 256
 #define B200_FINAL_BUF_KEYS 2048
 
@@ -302,7 +303,8 @@ __global__ void __launch_bounds__(256) final_merge_kernel(const ScanParams p, ui
 
 // ---- the kernel --------------------------------------------------------------------------------
 template <int METRIC, int STORE, int QB, int RB, int VARIANT>
-__global__ void __launch_bounds__(B200_SCAN_THREADS_MAX)
+__global__ void __launch_bounds__(VARIANT == B200_VARIANT_BULK ? B200_SCAN_THREADS_BULK : B200_SCAN_THREADS_LDG,
+                                  VARIANT == B200_VARIANT_BULK ? 1 : 4)
 scan_topk_kernel(const ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31;

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--nq", type=int, default=1)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--warps", action="store_true")
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--out", default="gpurun_out/sweep.jsonl")
     a = ap.parse_args()
@@ -63,6 +64,8 @@ def main():
     configs = []
     if a.quick:
         configs += [dict(scan_variant=0), dict(scan_variant=1), dict(scan_variant=2)]
+        if a.warps:
+            configs += [dict(scan_variant=1, scan_warps=w) for w in (10, 12, 16)]
     else:
         for dyn, ef, tr in itertools.product((1, 0), (0, 1), (0, 8)):
             configs.append(dict(scan_variant=1, scan_tile_rows=tr, scan_l2_evict_first=ef, scan_dynamic_tiles=dyn))
