@@ -111,3 +111,50 @@ def test_small_databases_use_the_tensor_path_too(b200, n, d, nq, k, metric):
     st = run_case(b200, n, d, nq, k, metric=metric, normalize=True)
     assert st["stat_gemm_used"] == 1
     assert st["stat_gemm_fallbacks"] <= max(2, nq // 4), st
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_batched_path_with_nan_inf_and_huge_rows(b200, metric):
+    """NaN rows never enter, +-inf follow the scan path's rules, and magnitudes that overflow bf16 make
+    the certificate fail safely (recomputed exactly) — results must equal the scan path bit for bit."""
+    n, d, nq, k = 70_000, 64, 9, 10
+    db = oracle.synth_rows(n, d, 77)
+    db[5, 3] = np.nan
+    db[6, 0] = np.inf
+    db[7, 0] = -np.inf
+    db[8] *= 1e30          # large but finite scores
+    db[9, 1] = 3.0e38      # rounds to inf in bf16
+    db[n - 1, 5] = np.nan
+    q = np.abs(oracle.synth_rows(nq, d, 78)) + 0.05
+    idx = b200.IndexFlat(d, metric)
+    idx.add(db)
+    D, I = idx.search(q, k)
+    assert idx.get_option("stat_gemm_used") == 1
+    idx.set_option("gemm_min_nq", 0)  # the scan path as the reference behaviour
+    Ds, Is = idx.search(q, k)
+    assert idx.get_option("stat_gemm_used") == 0
+    np.testing.assert_array_equal(I, Is)
+    np.testing.assert_array_equal(D, Ds)
+    Dw, Iw = oracle.search(metric, db, q, k, order=oracle.ORDER_DEVICE)
+    np.testing.assert_array_equal(I, Iw)
+    assert not np.isin(I, [5, n - 1]).any()
+
+
+def test_shadow_follows_adds_and_reset(b200):
+    d = 128
+    a, b = oracle.synth_rows(50_000, d, 1), oracle.synth_rows(30_000, d, 2)
+    q = oracle.synth_rows(6, d, 3)
+    idx = b200.IndexFlat(d, 0)
+    idx.add(a)
+    D1, I1 = idx.search(q, 10)
+    assert idx.get_option("stat_gemm_used") == 1
+    idx.add(b)  # the bf16 shadow must be rebuilt to cover the new rows
+    D2, I2 = idx.search(q, 10)
+    Dw, Iw = oracle.search(0, np.concatenate([a, b]), q, 10, order=oracle.ORDER_DEVICE)
+    np.testing.assert_array_equal(I2, Iw)
+    np.testing.assert_array_equal(D2, Dw)
+    idx.reset()
+    idx.add(b)
+    D3, I3 = idx.search(q, 10)
+    Dw3, Iw3 = oracle.search(0, b, q, 10, order=oracle.ORDER_DEVICE)
+    np.testing.assert_array_equal(I3, Iw3)
