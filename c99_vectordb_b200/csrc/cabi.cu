@@ -909,17 +909,21 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     CUtensorMap tm_q, tm_db;
     CKI(make_tmap_bf16(&tm_q, ix->g_qb, (uint64_t)((m_tiles + 1) / 2 * 2) * G3_BLOCK_M, (uint32_t)kpad, G3_BLOCK_M));
     CKI(make_tmap_bf16(&tm_db, ix->sh_rows, n, (uint32_t)kpad, G3_BLOCK_N / cg));
-    CK(cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3Cfg<1>::kSmemBytes));
-    CK(cudaFuncSetAttribute(gemm_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3Cfg<2>::kSmemBytes));
+    const bool masked = ix->cur_mask != nullptr;
+    typedef void (*GemmFn)(const CUtensorMap, const CUtensorMap, const GemmParams);
+    GemmFn gfn = cg == 1 ? (masked ? gemm_topk_kernel<1, true> : gemm_topk_kernel<1, false>)
+                         : (masked ? gemm_topk_kernel<2, true> : gemm_topk_kernel<2, false>);
+    const size_t gsmem = cg == 1 ? G3Cfg<1>::kSmemBytes : G3Cfg<2>::kSmemBytes;
+    CK(cudaFuncSetAttribute(gfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
     auto launch_gemm = [&](const GemmParams& g) -> int {
         if (cg == 1) {
-            gemm_topk_kernel<1><<<ix->num_sms, G3_THREADS, G3Cfg<1>::kSmemBytes, st>>>(tm_q, tm_db, g);
+            gfn<<<ix->num_sms, G3_THREADS, gsmem, st>>>(tm_q, tm_db, g);
         } else {
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
             cfg.gridDim = dim3((unsigned)(ix->num_sms / 2 * 2));
             cfg.blockDim = dim3(G3_THREADS);
-            cfg.dynamicSmemBytes = G3Cfg<2>::kSmemBytes;
+            cfg.dynamicSmemBytes = gsmem;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -928,7 +932,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            CK(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<2>, tm_q, tm_db, g));
+            CK(cudaLaunchKernelEx(&cfg, gfn, tm_q, tm_db, g));
         }
         ++ix->launches;
         CK(cudaGetLastError());
@@ -958,6 +962,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     gp.cand_rows = ix->g_cand;
     gp.cand_cap = cap;
     gp.tilemax = ix->g_tilemax;
+    gp.row_mask = ix->cur_mask;  // filtered search: excluded rows never become candidates
     // ---- pass 1: tile maxima over a strided sample of T tiles -> theta ----
     gp.mode = G3_MODE_TILEMAX;
     gp.tile_first = 0;
@@ -1128,7 +1133,7 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
     const bool fullrank = k >= ix->opt_fullrank_min_k || k > B200_FUSED_K_MAX;
     ix->stat_gemm_used = 0;
     if (!fullrank) {
-        if (!ix->cur_mask && !ix->xchg_active && gemm_eligible(ix, nq, k) && ix->sh_failed_rows != ix->ntotal) {
+        if (!ix->xchg_active && gemm_eligible(ix, nq, k) && ix->sh_failed_rows != ix->ntotal) {
             // K3 in blocks of at most 16384 queries (bounds the candidate scratch)
             int rc = 0;
             for (int64_t q0 = 0; q0 < nq && rc == 0; q0 += 16384) {

@@ -51,6 +51,7 @@ struct GemmParams {
     uint32_t* cand_rows;    // [nq, cand_cap]
     uint32_t cand_cap;
     float* tilemax;         // [nq, tile_count * 8]: one maximum per 32-row group (TILEMAX)
+    const uint32_t* row_mask;  // optional row bitmap (filtered search): excluded rows score -inf
 };
 
 // ---- PTX: TMA tensor load, tcgen05 ------------------------------------------------------------
@@ -191,7 +192,7 @@ struct G3Cfg {
 // cores share the row operand, which halves shared-memory traffic per SM (the cta_group::1 form is
 // capped near 2/3 of peak by the 128 B/cycle smem port: 96 B/cycle of operand reads + 96 B/cycle of
 // TMA fills).  Only the pair's leader (rank 0) issues MMAs; both CTAs run TMA and the epilogue.
-template <int CG>
+template <int CG, bool MASKED>
 __global__ void __launch_bounds__(G3_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
                  const GemmParams p) {
@@ -344,11 +345,15 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     tc_wait_ld();
                     gmax[c0 / 32] = -INFINITY;
                     if (c0 >= live_cols) continue;  // rows past the end of the database (zero filled by TMA)
+                    // MASKED: one aligned mask word covers these 32 rows (tiles start at multiples of 256)
+                    uint32_t mw = 0xFFFFFFFFu;
+                    if (MASKED) mw = __ldg(p.row_mask + ((row0 + c0) >> 5));
                     float m = -INFINITY;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float s = __uint_as_float(v[j]);
                         if (c0 + j >= live_cols) s = -INFINITY;
+                        if (MASKED && !((mw >> j) & 1u)) s = -INFINITY;
                         m = fmaxf(m, s);
                     }
                     gmax[c0 / 32] = m;
@@ -359,6 +364,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             hit |= (__uint_as_float(v[j]) > theta && c0 + j < live_cols) ? (1u << j) : 0u;
+                        if (MASKED) hit &= mw;
                         while (hit) {
                             const int j = __ffs(hit) - 1;
                             hit &= hit - 1;

@@ -159,7 +159,27 @@ __device__ __forceinline__ void final_merge_one(const ScanParams& p, int qi, uin
     const uint32_t B = p.scratch_keys;
     for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) scratch[i] = 0ull;
     if (threadIdx.x == 0) *sctr = (unsigned)k;
+    // Pre-filter: a CTA whose list is full proves that k candidates are at least as good as its k-th
+    // key, so the global k-th best cannot be below tau0 = max over CTAs of their k-th keys.  Typically
+    // only a few dozen of the nctas*k keys survive, so the sort below handles 32-128 keys, not 2048.
+    __shared__ unsigned long long s_tau0;
+    if (threadIdx.x == 0) s_tau0 = 0ull;
     __syncthreads();
+    {
+        uint64_t t0 = 0ull;
+        for (uint32_t c = threadIdx.x; c < nctas; c += blockDim.x) {
+            uint64_t kth = __ldcg(p.partials + ((size_t)c * QB + qi) * k + (k - 1));
+            t0 = kth > t0 ? kth : t0;
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            uint64_t o = __shfl_xor_sync(B200_FULL_MASK, t0, m);
+            t0 = o > t0 ? o : t0;
+        }
+        if ((threadIdx.x & 31) == 0 && t0) atomicMax(&s_tau0, (unsigned long long)t0);
+    }
+    __syncthreads();
+    const uint64_t tau0 = s_tau0 ? (uint64_t)s_tau0 - 1ull : 0ull;  // keep keys >= max k-th key
     uint32_t cta = 0;
     while (cta < nctas) {
         uint32_t filled = *sctr;
@@ -167,6 +187,7 @@ __device__ __forceinline__ void final_merge_one(const ScanParams& p, int qi, uin
         if (fit == 0) fit = 1;
         uint32_t take = nctas - cta < fit ? nctas - cta : fit;
         uint64_t tau_now = scratch[k - 1];
+        if (tau0 > tau_now) tau_now = tau0;
         __syncthreads();
         if (tau_now == 0ull) {
             for (uint32_t i = threadIdx.x; i < take * (uint32_t)k; i += blockDim.x) {

@@ -111,7 +111,8 @@ int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_
 /* filtered search (push memo's metadata filter down into the scan instead of
  * k = ntotal + Python post-filter, memo_cli.py:291, :491-521).  mask is a bitmap over ROW
  * POSITIONS, ceil(ntotal/32) uint32 words, bit (r & 31) of word r >> 5 set = row r may be returned;
- * NULL = no filter.  Always served by the exact scan kernels. */
+ * NULL = no filter.  Single queries use the scan kernel, batches the tensor-core path (the bitmap is
+ * applied in both epilogues); results are exact either way. */
 int b200_index_search_masked(b200_index* ix, const float* q_host, int64_t nq, int64_t k,
                              const uint32_t* mask_host, float* D_host, int64_t* I_host);
 int b200_index_search_masked_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k,

@@ -158,3 +158,28 @@ def test_shadow_follows_adds_and_reset(b200):
     D3, I3 = idx.search(q, 10)
     Dw3, Iw3 = oracle.search(0, b, q, 10, order=oracle.ORDER_DEVICE)
     np.testing.assert_array_equal(I3, Iw3)
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_batched_masked_search(b200, metric):
+    """Filter push-down on the tensor-core path: excluded rows never become candidates."""
+    n, d, nq, k = 90_000, 128, 40, 10
+    db, q = oracle.synth_rows(n, d, 5), oracle.synth_rows(nq, d, 6)
+    db[1000:1100] = db[2000:2100]
+    ids = np.arange(n, dtype=np.int64) + 7
+    idx = b200.IndexIDMap2(b200.IndexFlat(d, metric))
+    idx.add_with_ids(db, ids)
+    rng = np.random.default_rng(9)
+    for frac in (0.5, 0.05):
+        mask = rng.random(n) < frac
+        rows = np.nonzero(mask)[0]
+        D, I = idx.search(q, k, row_mask=mask)
+        assert idx.index.get_option("stat_gemm_used") == 1
+        Dw, Iw = oracle.search(metric, db[rows], q, k, ids=ids[rows], order=oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)
+    # fewer allowed rows than k: the certificate cannot hold, the exact scan pads with -1
+    mask = np.zeros(n, dtype=bool)
+    mask[[5, 77, 4000]] = True
+    D, I = idx.search(q, k, row_mask=mask)
+    assert (I[:, 3:] == -1).all() and set(I[0, :3].tolist()) == {12, 84, 4007}
