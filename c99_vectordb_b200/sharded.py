@@ -113,25 +113,42 @@ class ShardedIndexFlat:
 
         if self.world == 1 or self.device.type != "cuda":
             return False
+        import torch
+
         L = _cabi.load()
-        nbytes = 2 * self.world * int(L.b200_exchange_slot_bytes())
-        handle = C.create_string_buffer(64)
-        mine = C.c_void_p()
-        _cabi.check(L.b200_ipc_alloc(C.byref(mine), nbytes, handle))
-        handles = [None] * self.world
-        dist.all_gather_object(handles, handle.raw, group=self.group)
+        ok, err = 1, ""
         peers = (C.c_void_p * self.world)()
-        for g in range(self.world):
-            if g == self.rank:
-                peers[g] = mine.value
-            else:
-                p = C.c_void_p()
-                _cabi.check(L.b200_ipc_open(handles[g], C.byref(p)))
-                peers[g] = p.value
-        _cabi.check(L.b200_index_set_exchange(self.local.index._h, self.world, self.rank, peers))
-        dist.barrier(group=self.group)
-        self._fused = True
-        return True
+        try:
+            nbytes = 2 * self.world * int(L.b200_exchange_slot_bytes())
+            handle = C.create_string_buffer(64)
+            mine = C.c_void_p()
+            _cabi.check(L.b200_ipc_alloc(C.byref(mine), nbytes, handle))
+            raw = handle.raw
+        except RuntimeError as e:  # keep the collective below balanced even if this rank failed
+            ok, err, raw = 0, str(e), b"\0" * 64
+        handles = [None] * self.world
+        dist.all_gather_object(handles, raw, group=self.group)
+        if ok:
+            try:
+                for g in range(self.world):
+                    if g == self.rank:
+                        peers[g] = mine.value
+                    else:
+                        p = C.c_void_p()
+                        _cabi.check(L.b200_ipc_open(handles[g], C.byref(p)))
+                        peers[g] = p.value
+                _cabi.check(L.b200_index_set_exchange(self.local.index._h, self.world, self.rank, peers))
+            except RuntimeError as e:
+                ok, err = 0, str(e)
+        # all ranks or none: a single rank without peer mappings would deadlock the others
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self._fused = bool(flag.item())
+        if not self._fused and err:
+            import sys
+
+            print(f"[b200] fused exchange unavailable on rank {self.rank} ({err}); using NCCL", file=sys.stderr)
+        return self._fused
 
     def _fused_ok(self, nq: int, k: int) -> bool:
         # The fused exchange lives in the scan kernel's tail and serves single queries (the latency
