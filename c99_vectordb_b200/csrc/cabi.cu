@@ -101,6 +101,7 @@ struct b200_index {
     uint32_t* g_cand = nullptr;
     int* g_cert = nullptr;
     size_t g_qb_cap = 0, g_q_cap = 0, g_tilemax_cap = 0, g_cand_cap = 0;
+    cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // pass brackets of the last batched search
     uint8_t* up_pin[2] = {nullptr, nullptr};  // pinned upload ring for bulk host adds
     cudaEvent_t up_ev[2] = {nullptr, nullptr};
     size_t up_chunk = 0;
@@ -108,7 +109,8 @@ struct b200_index {
     uint8_t** xchg_peers_dev = nullptr;  // device array of world peer buffer pointers
     int xchg_world = 0, xchg_rank = 0;
     uint32_t xchg_epoch = 0;
-    int* xchg_status = nullptr;
+    int* xchg_status = nullptr;             // device view of the host-mapped flag below
+    volatile int* xchg_status_host = nullptr;  // set by a kernel whose peers never arrived
     bool xchg_active = false;            // the search in flight exchanges
     const uint32_t* cur_mask = nullptr;  // row bitmap of the search in flight (device), or null
     uint32_t* mask_dev = nullptr;        // staging for host masks
@@ -120,6 +122,15 @@ static int use_device(b200_index* ix) {
     CK(cudaSetDevice(ix->device));
     return 0;
 }
+
+// device scratch that must not outlive an early error return
+struct DevTmp {
+    void* p = nullptr;
+    ~DevTmp() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+};
 
 template <typename T>
 static int grow(T** p, size_t* cap, size_t need) {
@@ -200,7 +211,6 @@ extern "C" int b200_index_destroy(b200_index* ix) {
         if (ix->up_ev[i]) cudaEventDestroy(ix->up_ev[i]);
     }
     cudaFree(ix->xchg_peers_dev);
-    cudaFree(ix->xchg_status);
     cudaFree(ix->mask_dev);
     cudaFree(ix->sh_rows);
     cudaFree(ix->sh_norm2);
@@ -212,6 +222,9 @@ extern "C" int b200_index_destroy(b200_index* ix) {
     cudaFree(ix->g_count);
     cudaFree(ix->g_cand);
     cudaFree(ix->g_cert);
+    for (int i = 0; i < 4; ++i)
+        if (ix->g_ev[i]) cudaEventDestroy(ix->g_ev[i]);
+    if (ix->xchg_status_host) cudaFreeHost((void*)ix->xchg_status_host);
     if (ix->pin) cudaFreeHost(ix->pin);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
@@ -938,8 +951,9 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
         CK(cudaGetLastError());
         return 0;
     };
-    cudaEvent_t ev[4];
-    for (auto& e : ev) CK(cudaEventCreate(&e));
+    cudaEvent_t* ev = ix->g_ev;
+    for (int i = 0; i < 4; ++i)
+        if (!ev[i]) CK(cudaEventCreate(&ev[i]));
     GemmParams gp;
     memset(&gp, 0, sizeof gp);
     gp.nq = (uint32_t)nq;
@@ -1038,7 +1052,6 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); ix->stat_gemm_pass1_us = (int64_t)(ms * 1e3);
     CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); ix->stat_gemm_pass2_us = (int64_t)(ms * 1e3);
     CK(cudaEventElapsedTime(&ms, ev[2], ev[3])); ix->stat_gemm_rerank_us = (int64_t)(ms * 1e3);
-    for (auto& e : ev) cudaEventDestroy(e);
     std::vector<int64_t> bad;
     int64_t cand_total = 0;
     for (int64_t i = 0; i < nq; ++i) {
@@ -1056,10 +1069,13 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     if (!bad.empty()) {
         // gather the failed queries, search them exactly 8 at a time, scatter the results back
         const size_t nb = bad.size();
-        float* qtmp = nullptr; float* Dtmp = nullptr; int64_t* Itmp = nullptr;
-        CK(cudaMalloc((void**)&qtmp, nb * ix->d * 4));
-        CK(cudaMalloc((void**)&Dtmp, nb * (size_t)k * 4));
-        CK(cudaMalloc((void**)&Itmp, nb * (size_t)k * 8));
+        DevTmp tq, tD, tI;
+        CK(tq.alloc(nb * ix->d * 4));
+        CK(tD.alloc(nb * (size_t)k * 4));
+        CK(tI.alloc(nb * (size_t)k * 8));
+        float* qtmp = (float*)tq.p;
+        float* Dtmp = (float*)tD.p;
+        int64_t* Itmp = (int64_t*)tI.p;
         for (size_t j = 0; j < nb; ++j)
             CK(cudaMemcpyAsync(qtmp + j * ix->d, q_dev + (size_t)bad[j] * ix->d, (size_t)ix->d * 4, cudaMemcpyDeviceToDevice, st));
         // first retry on the tensor cores with a 3x wider threshold (one more sweep of the shadow serves
@@ -1077,8 +1093,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
                 cudaMemcpyAsync(D_dev + (size_t)bad[j] * k, Dtmp + j * k, (size_t)k * 4, cudaMemcpyDeviceToDevice, st);
                 cudaMemcpyAsync(I_dev + (size_t)bad[j] * k, Itmp + j * k, (size_t)k * 8, cudaMemcpyDeviceToDevice, st);
             }
-        cudaStreamSynchronize(st);
-        cudaFree(qtmp); cudaFree(Dtmp); cudaFree(Itmp);
+        cudaStreamSynchronize(st);  // the temporaries are released when this scope ends
         if (rc) return rc;
     }
     return 0;
@@ -1296,9 +1311,12 @@ extern "C" int b200_index_set_exchange(b200_index* ix, int world, int rank, void
     ix->xchg_peers_dev = nullptr;
     CK(cudaMalloc((void**)&ix->xchg_peers_dev, (size_t)world * sizeof(void*)));
     CK(cudaMemcpy(ix->xchg_peers_dev, peer_bufs, (size_t)world * sizeof(void*), cudaMemcpyHostToDevice));
-    if (!ix->xchg_status) {
-        CK(cudaMalloc((void**)&ix->xchg_status, sizeof(int)));
-        CK(cudaMemset(ix->xchg_status, 0, sizeof(int)));
+    if (!ix->xchg_status_host) {
+        int* h = nullptr;
+        CK(cudaHostAlloc((void**)&h, sizeof(int), cudaHostAllocMapped));
+        *h = 0;
+        CK(cudaHostGetDevicePointer((void**)&ix->xchg_status, h, 0));
+        ix->xchg_status_host = h;
     }
     ix->xchg_world = world;
     ix->xchg_rank = rank;
@@ -1311,6 +1329,7 @@ extern "C" int b200_index_search_exchange_dev(b200_index* ix, const float* q_dev
     if (!ix->xchg_peers_dev) return fail("b200_index_set_exchange has not been called");
     if (k > B200_FUSED_K_MAX || k >= ix->opt_fullrank_min_k) return fail("fused exchange needs k <= %d", B200_FUSED_K_MAX);
     if (ix->ntotal == 0) return fail("fused exchange needs at least one row on every rank");
+    if (*ix->xchg_status_host) return fail("fused exchange: a peer GPU did not deliver its results in time during an earlier search");
     ix->xchg_active = true;
     int rc = b200_index_search_dev(ix, q_dev, nq, k, D_dev, I_dev, stream);
     ix->xchg_active = false;

@@ -264,7 +264,7 @@ class IndexIDMap(Index):
     def __init__(self, index: IndexFlat):
         if not isinstance(index, IndexFlat):
             raise RuntimeError("IndexIDMap: only flat base indexes are supported")
-        if index.ntotal != 0 and not getattr(index, "_idmap_adopt", False):
+        if index.ntotal != 0:
             raise RuntimeError("index must be empty on input")  # as faiss [upstream]
         self.index = index
         self.own_fields = True
