@@ -52,6 +52,7 @@ static int fail(const char* fmt, ...) {
 struct b200_index {
     int d = 0, d_pad = 0, metric = 0, store = 0, device = 0;
     size_t pitch = 0;  // bytes per stored row
+    int lpr = 32;      // lanes sharing a row in the scan arithmetic: 16 for rows of <= 48 sixteen-byte chunks
     uint8_t* rows = nullptr;
     int64_t ntotal = 0, capacity = 0;
     int64_t* ids = nullptr;
@@ -177,6 +178,10 @@ extern "C" int b200_index_create(b200_index** out, int d, int metric, int store,
     ix->device = device;
     ix->d_pad = store == B200_STORE_F32 ? (d + 3) / 4 * 4 : (d + 7) / 8 * 8;
     ix->pitch = (size_t)ix->d_pad * (store == B200_STORE_F32 ? 4 : 2);
+    {
+        const size_t nvec = ix->pitch / 16;
+        ix->lpr = (nvec <= 48 && nvec % 16 == 0) ? 16 : 32;  // part of the index's numerics: fixed at creation
+    }
     ix->num_sms = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
@@ -567,10 +572,11 @@ struct ScanPlan {
 
 typedef void (*ScanFn)(const ScanParams);
 #define SCAN_RB 4
-static ScanFn pick_scan(int metric, int store, int qb, int variant) {
-#define SC(M, S, Q, V) \
-    if (metric == M && store == S && qb == Q && variant == V) return scan_topk_kernel<M, S, Q, SCAN_RB, V>;
-#define SC_Q(M, S, V) SC(M, S, 1, V) SC(M, S, 2, V) SC(M, S, 4, V) SC(M, S, 8, V)
+// 32 lanes per row: query blocks 1/2/4/8.  16 lanes per row (short rows): query blocks 1 and 8 only.
+static ScanFn pick_scan(int metric, int store, int qb, int variant, int lpr) {
+#define SC(M, S, Q, V, L) \
+    if (metric == M && store == S && qb == Q && variant == V && lpr == L) return scan_topk_kernel<M, S, Q, SCAN_RB, V, L>;
+#define SC_Q(M, S, V) SC(M, S, 1, V, 32) SC(M, S, 2, V, 32) SC(M, S, 4, V, 32) SC(M, S, 8, V, 32) SC(M, S, 1, V, 16) SC(M, S, 8, V, 16)
 #define SC_S(M, V) SC_Q(M, 0, V) SC_Q(M, 1, V)
     SC_S(0, B200_VARIANT_BULK) SC_S(1, B200_VARIANT_BULK) SC_S(0, B200_VARIANT_LDG) SC_S(1, B200_VARIANT_LDG)
 #undef SC_S
@@ -600,15 +606,16 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
     const int qstride = (ix->d_pad + 7) / 8 * 8;
     const int kk = fullrank ? 1 : k;
     const size_t budget = ix->smem_optin - 1024;
+    const uint32_t step_rows = SCAN_RB * (32u / (uint32_t)ix->lpr);  // rows one warp step covers
     int variant = (int)ix->opt_variant;
-    // AUTO (measured over d = 64..2048, fp32 and bf16: profiles/README.md, r1_sweep11_*): the
-    // TMA-staged ring with dynamic tiles and as many warps as fit (<= 16) x 2 stages.  Short rows and
-    // bf16 rows carry more instructions per byte and want the extra warps (bf16 d=1024: 1.09-1.12 of
-    // the measured peak vs 1.02 for direct loads); long rows still win with 3-4 warps (d=2048: 1.12
-    // vs 1.03).  Rows under 768 bytes (fewer than 48 16-byte chunks: lanes idle in both variants,
-    // 0.5-0.9) go to the direct-load variant with its 32 resident warps/SM.
+    // AUTO (measured over d = 64..2048, fp32 and bf16: profiles/README.md, r1_sweep11_*, r1_sweep13_*):
+    // the TMA-staged ring with dynamic tiles and as many warps as fit (<= 16) x 2 stages.  Short rows
+    // and bf16 rows carry more instructions per byte and want the extra warps (bf16 d=1024: 1.09-1.12
+    // of the measured peak vs 1.02 for direct loads); long rows still win with 3-4 warps (d=2048: 1.12
+    // vs 1.03).  Rows under 512 bytes go to the direct-load variant with its 32 resident warps/SM
+    // (d=64 fp32: 0.89 vs 0.86).
     const bool auto_variant = variant == B200_SCAN_AUTO;
-    if (auto_variant) variant = ix->pitch >= 768 ? B200_VARIANT_BULK : B200_VARIANT_LDG;
+    if (auto_variant) variant = ix->pitch >= 512 ? B200_VARIANT_BULK : B200_VARIANT_LDG;
     if (variant == B200_VARIANT_BULK) {
         int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_BULK / 32);
         const int nw_min = auto_variant ? 3 : 1;
@@ -620,11 +627,11 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
         for (; nw >= nw_min && !ok; --nw) {
             uint32_t m_pref;
             if (ix->opt_tile_rows > 0)
-                m_pref = (uint32_t)((ix->opt_tile_rows + SCAN_RB - 1) / SCAN_RB);
+                m_pref = (uint32_t)((ix->opt_tile_rows + step_rows - 1) / step_rows);
             else
-                m_pref = (uint32_t)std::max(1.0, 12288.0 / ((double)SCAN_RB * ix->pitch) + 0.5);
+                m_pref = (uint32_t)std::max(1.0, 12288.0 / ((double)step_rows * ix->pitch) + 0.5);
             for (uint32_t m = m_pref; m >= 1 && !ok; --m) {
-                uint32_t tr = m * SCAN_RB;
+                uint32_t tr = m * step_rows;
                 uint64_t tile_bytes = (uint64_t)tr * ix->pitch;
                 if (tile_bytes > (1u << 19)) continue;  // mbarrier tx-count headroom
                 uint32_t scratch = std::max<uint32_t>(B200_FINAL_BUF_KEYS, next_pow2((uint32_t)(nw * kk)));
@@ -660,14 +667,14 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
             if (smem > budget) continue;
             pl.variant = B200_VARIANT_LDG;
             pl.nw = nw;
-            pl.tile_rows = SCAN_RB;
+            pl.tile_rows = step_rows;
             pl.stages = 0;
             pl.tile_bytes = 0;
             pl.scratch_keys = scratch;
             pl.smem = smem;
             break;
         }
-        ScanFn fn = pick_scan(ix->metric, ix->store, qb, B200_VARIANT_LDG);
+        ScanFn fn = pick_scan(ix->metric, ix->store, qb, B200_VARIANT_LDG, ix->lpr);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl.nw * 32, pl.smem));
@@ -739,7 +746,7 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
         CKI(grow(&ix->partials, &ix->partials_cap, need));
     }
     p.partials = ix->partials;
-    ScanFn fn = pick_scan(ix->metric, ix->store, pl.qb, pl.variant);
+    ScanFn fn = pick_scan(ix->metric, ix->store, pl.qb, pl.variant, ix->lpr);
     if (!fn) return fail("no scan kernel for metric=%d store=%d qb=%d variant=%d", ix->metric, ix->store, pl.qb, pl.variant);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     fn<<<pl.grid, pl.nw * 32, pl.smem, st>>>(p);
@@ -791,7 +798,8 @@ static int fullrank_one(b200_index* ix, const uint32_t* hi_keys, int64_t k, floa
     return 0;
 }
 
-static int pick_qb(int64_t remaining, int64_t forced) {
+static int pick_qb(int64_t remaining, int64_t forced, int lpr) {
+    if (lpr != 32) return remaining >= 2 ? 8 : 1;  // short-row kernels exist for query blocks 1 and 8
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return (int)forced;
     if (remaining >= 8) return 8;
     if (remaining > 2) return 4;
@@ -1016,6 +1024,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     rp.store = ix->store;
     rp.d = ix->d;
     rp.qstride = (ix->d_pad + 7) / 8 * 8;
+    rp.lpr = ix->lpr;
     rp.q = q_dev;
     rp.cand_rows = ix->g_cand;
     rp.cand_count = ix->g_count;
@@ -1104,7 +1113,7 @@ static int search_scan_block(b200_index* ix, const float* q_dev, int64_t nq, int
                              cudaStream_t st) {
     int64_t q0 = 0;
     while (q0 < nq) {
-        int qb = pick_qb(nq - q0, ix->opt_qb);
+        int qb = pick_qb(nq - q0, ix->opt_qb, ix->lpr);
         int nqb = (int)std::min<int64_t>(qb, nq - q0);
         ScanPlan pl;
         CKI(plan_scan(ix, qb, (int)k, false, &pl));
@@ -1164,7 +1173,7 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
     const uint64_t n = (uint64_t)ix->ntotal;
     int64_t q0 = 0;
     while (q0 < nq) {
-        int qb = pick_qb(nq - q0, ix->opt_qb);
+        int qb = pick_qb(nq - q0, ix->opt_qb, ix->lpr);
         int nqb = (int)std::min<int64_t>(qb, nq - q0);
         if (ix->fr_hi_cap < (size_t)qb * n) {
             CK(cudaStreamSynchronize(st));

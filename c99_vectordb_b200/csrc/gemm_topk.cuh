@@ -493,6 +493,7 @@ struct RerankParams {
     int store;             // 0 fp32 rows, 1 bf16 rows
     int d;
     int qstride;           // floats per staged query (multiple of 8)
+    int lpr;               // lanes sharing a row in the scan arithmetic (32, or 16 for short rows)
     const float* q;        // [nq, d] fp32 queries (the originals, not the bf16 shadow)
     const uint32_t* cand_rows;
     const unsigned int* cand_count;
@@ -528,7 +529,9 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
         const uint32_t row = p.cand_rows[(size_t)qi * p.cand_cap + j];
         const uint8_t* rp = p.rows + (uint64_t)row * p.pitch_bytes;
         float acc = 0.0f;
-        for (uint32_t ch = lane; ch < p.nvec; ch += 32) {
+        // lanes >= lpr stay at +0: adding them in the 32-lane butterfly below is exact, so the result
+        // equals the lpr-lane butterfly of the scan kernel
+        for (uint32_t ch = lane; ch < p.nvec && lane < p.lpr; ch += p.lpr) {
             uint4 raw = ldg_nc_v4(rp + (size_t)ch * 16);
             auto step = [&](uint32_t bits, float qv) {  // same element arithmetic as scan_topk.cuh acc1<>
                 const float v = __uint_as_float(bits);

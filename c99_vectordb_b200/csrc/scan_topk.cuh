@@ -12,9 +12,9 @@
 //                  into registers.  Universal fallback (any row pitch) and the A/B partner for
 //                  the ncu evidence.
 //
-// Both produce bit-identical scores: lane l accumulates 16-byte chunks l, l+32, ... of the row
-// in ascending element order with fmaf, then a 16/8/4/2/1 xor butterfly
-// (oracle/flat_oracle.c: oracle_score_device_order restates exactly this order).
+// Both produce bit-identical scores: lane l of the LPR lanes sharing a row accumulates 16-byte chunks
+// l, l+LPR, ... in ascending element order with fmaf, then an xor butterfly LPR/2 ... 1 (LPR = 32, or 16
+// for rows of <= 48 chunks; oracle/flat_oracle.c: score_device restates exactly this order).
 //
 // Top-k: per warp an unsorted k-entry list of 64-bit keys in shared memory plus the running
 // threshold tau = worst key kept; a row is inserted only when its key beats tau (rare after
@@ -323,12 +323,18 @@ __global__ void __launch_bounds__(256) final_merge_kernel(const ScanParams p, ui
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
-template <int METRIC, int STORE, int QB, int RB, int VARIANT>
+// LPR = lanes that share one row: 32 normally; 16 for rows of <= 48 sixteen-byte chunks (<= 768 B), where a
+// full warp per row would leave lanes idle — the warp then works on SETS = 2 row sets of RB rows at once
+// (lanes 0-15 on the first, 16-31 on the second) and the butterfly has 4 rounds (8,4,2,1).
+template <int METRIC, int STORE, int QB, int RB, int VARIANT, int LPR>
 __global__ void __launch_bounds__(VARIANT == B200_VARIANT_BULK ? B200_SCAN_THREADS_BULK : B200_SCAN_THREADS_LDG,
-                                  VARIANT == B200_VARIANT_BULK ? 1 : 4)
+                                  VARIANT == B200_VARIANT_BULK ? 1 : (QB >= 4 ? 2 : 4))  // QB*RB accumulators need registers
 scan_topk_kernel(const ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int SETS = 32 / LPR;      // row sets a warp processes concurrently
+    constexpr int RSTEP = RB * SETS;    // rows per warp step
     const int lane = threadIdx.x & 31;
+    const int set = lane / LPR, sl = lane % LPR;
     const int warp = threadIdx.x >> 5;
     const int nw = blockDim.x >> 5;
     const bool fullrank = (p.score_keys != nullptr);
@@ -460,26 +466,27 @@ scan_topk_kernel(const ScanParams p) {
         }
         const uint64_t tile_row0 = (uint64_t)t * TR;
         const uint32_t rows_in_tile = (uint32_t)(p.n - tile_row0 < TR ? p.n - tile_row0 : TR);
-        for (uint32_t g = 0; g < rows_in_tile; g += RB) {
+        for (uint32_t g = 0; g < rows_in_tile; g += RSTEP) {
             float acc[QB][RB];
 #pragma unroll
             for (int qi = 0; qi < QB; ++qi)
 #pragma unroll
                 for (int r = 0; r < RB; ++r) acc[qi][r] = 0.0f;
 
+            const uint32_t g_set = g + (uint32_t)set * RB;  // first row (within the tile) of this lane's set
             const uint8_t* rp[RB];
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
                 if (VARIANT == B200_VARIANT_BULK) {
-                    rp[r] = tile_smem + (size_t)(g + r) * p.pitch_bytes;  // stale rows are discarded below
+                    rp[r] = tile_smem + (size_t)(g_set + r) * p.pitch_bytes;  // stale rows are discarded below
                 } else {
-                    uint64_t row = tile_row0 + g + r;
+                    uint64_t row = tile_row0 + g_set + r;
                     if (row >= p.n) row = p.n - 1;
                     rp[r] = p.rows + row * p.pitch_bytes;
                 }
             }
 #pragma unroll 2
-            for (uint32_t c = lane; c < nvec; c += 32) {
+            for (uint32_t c = sl; c < nvec; c += LPR) {
                 uint4 raw[RB];
 #pragma unroll
                 for (int r = 0; r < RB; ++r) {
@@ -506,30 +513,31 @@ scan_topk_kernel(const ScanParams p) {
                 }
             }
             if (QB == 1 && RB == 4 && !fullrank) {
-                // Transposing butterfly: after the xor-16 and xor-8 rounds each lane carries ONE row's
-                // partial sum (row = (lane >> 3) & 3), then xor 4/2/1 finish it.  The additions are
-                // the same pairs as four separate butterflies, so scores stay bit-identical; 6 shuffles
-                // instead of 20, and one ballot decides whether any row beats the threshold.
-                const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
-                float k0 = up16 ? acc[0][2] : acc[0][0], k1 = up16 ? acc[0][3] : acc[0][1];
-                float s0 = up16 ? acc[0][0] : acc[0][2], s1 = up16 ? acc[0][1] : acc[0][3];
-                k0 += __shfl_xor_sync(B200_FULL_MASK, s0, 16);
-                k1 += __shfl_xor_sync(B200_FULL_MASK, s1, 16);
-                float kk = up8 ? k1 : k0, ss = up8 ? k0 : k1;
-                kk += __shfl_xor_sync(B200_FULL_MASK, ss, 8);
-                kk += __shfl_xor_sync(B200_FULL_MASK, kk, 4);
-                kk += __shfl_xor_sync(B200_FULL_MASK, kk, 2);
-                kk += __shfl_xor_sync(B200_FULL_MASK, kk, 1);
-                const uint32_t myr = ((uint32_t)lane >> 3) & 3u;
-                const uint64_t myrow = tile_row0 + g + myr;
-                bool live = (g + myr < rows_in_tile) && b200_score_valid<METRIC>(kk);
+                // Transposing butterfly over the LPR lanes of a row set: after the first two rounds
+                // (xor LPR/2, xor LPR/4) each lane carries ONE row's partial sum, the remaining rounds
+                // finish it.  The additions are the same pairs as four separate butterflies, so scores
+                // stay bit-identical; 6 (5) shuffles instead of 20 (16), and one ballot decides whether
+                // any of the warp's RSTEP rows beats the threshold.
+                constexpr int H = LPR / 2, Q4 = LPR / 4;
+                const bool upH = (sl & H) != 0, upQ = (sl & Q4) != 0;
+                float k0 = upH ? acc[0][2] : acc[0][0], k1 = upH ? acc[0][3] : acc[0][1];
+                float s0 = upH ? acc[0][0] : acc[0][2], s1 = upH ? acc[0][1] : acc[0][3];
+                k0 += __shfl_xor_sync(B200_FULL_MASK, s0, H);
+                k1 += __shfl_xor_sync(B200_FULL_MASK, s1, H);
+                float kk = upQ ? k1 : k0, ss = upQ ? k0 : k1;
+                kk += __shfl_xor_sync(B200_FULL_MASK, ss, Q4);
+#pragma unroll
+                for (int m = Q4 / 2; m >= 1; m >>= 1) kk += __shfl_xor_sync(B200_FULL_MASK, kk, m);
+                const uint32_t myr = (upH ? 2u : 0u) + (upQ ? 1u : 0u);
+                const uint64_t myrow = tile_row0 + g_set + myr;
+                bool live = (g_set + myr < rows_in_tile) && b200_score_valid<METRIC>(kk);
                 if (p.row_mask && live) live = (__ldg(p.row_mask + (myrow >> 5)) >> (myrow & 31)) & 1u;
                 const uint64_t mykey = b200_make_key<METRIC>(kk, (uint32_t)myrow);
                 unsigned hits = __ballot_sync(B200_FULL_MASK, live && mykey > tau[0]);
                 while (hits) {  // rare: a row beats the warp's current k-th best
                     const int src = __ffs(hits) - 1;
                     const uint64_t key = __shfl_sync(B200_FULL_MASK, mykey, src);
-                    hits &= ~(0xFFu << (src & ~7));  // the 8 lanes of that row carry the same key
+                    hits &= ~(((1u << Q4) - 1u) << (src & ~(Q4 - 1)));  // the Q4 lanes of that row carry the same key
                     if (key > tau[0]) warp_list_insert(my_lists, k, lane, key, tau[0], tau_pos[0]);
                 }
                 continue;
@@ -537,25 +545,33 @@ scan_topk_kernel(const ScanParams p) {
 #pragma unroll
             for (int qi = 0; qi < QB; ++qi)
 #pragma unroll
-                for (int r = 0; r < RB; ++r) acc[qi][r] = warp_sum_xor(acc[qi][r]);
+                for (int r = 0; r < RB; ++r) {
+                    float v = acc[qi][r];
+#pragma unroll
+                    for (int m = LPR / 2; m >= 1; m >>= 1) v += __shfl_xor_sync(B200_FULL_MASK, v, m);
+                    acc[qi][r] = v;  // every lane of a row set now holds that set's score
+                }
 
 #pragma unroll
-            for (int qi = 0; qi < QB; ++qi) {
-                if (qi >= p.nqb) break;
+            for (int st = 0; st < SETS; ++st) {  // warp-uniform walk over the row sets
 #pragma unroll
-                for (int r = 0; r < RB; ++r) {
-                    if (g + r >= rows_in_tile) break;
-                    const uint64_t row = tile_row0 + g + r;
-                    const float sc = acc[qi][r];
-                    bool valid = b200_score_valid<METRIC>(sc);
-                    if (p.row_mask && valid) valid = (__ldg(p.row_mask + (row >> 5)) >> (row & 31)) & 1u;
-                    if (fullrank) {
-                        if (lane == 0)
-                            p.score_keys[(size_t)qi * p.n + row] = valid ? b200_key_hi<METRIC>(sc) : 0u;
-                    } else if (valid) {
-                        uint64_t key = b200_make_key<METRIC>(sc, (uint32_t)row);
-                        if (key > tau[qi])
-                            warp_list_insert(my_lists + (size_t)qi * k, k, lane, key, tau[qi], tau_pos[qi]);
+                for (int qi = 0; qi < QB; ++qi) {
+                    if (qi >= p.nqb) break;
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) {
+                        if (g + st * RB + r >= rows_in_tile) break;
+                        const uint64_t row = tile_row0 + g + st * RB + r;
+                        const float sc = SETS == 1 ? acc[qi][r] : __shfl_sync(B200_FULL_MASK, acc[qi][r], st * LPR);
+                        bool valid = b200_score_valid<METRIC>(sc);
+                        if (p.row_mask && valid) valid = (__ldg(p.row_mask + (row >> 5)) >> (row & 31)) & 1u;
+                        if (fullrank) {
+                            if (lane == 0)
+                                p.score_keys[(size_t)qi * p.n + row] = valid ? b200_key_hi<METRIC>(sc) : 0u;
+                        } else if (valid) {
+                            uint64_t key = b200_make_key<METRIC>(sc, (uint32_t)row);
+                            if (key > tau[qi])
+                                warp_list_insert(my_lists + (size_t)qi * k, k, lane, key, tau[qi], tau_pos[qi]);
+                        }
                     }
                 }
             }

@@ -51,7 +51,8 @@
 #define ORACLE_METRIC_IP 0
 #define ORACLE_METRIC_L2 1
 #define ORACLE_ORDER_SIMD 0
-#define ORACLE_ORDER_DEVICE 1
+#define ORACLE_ORDER_DEVICE 1   /* 32 lanes per row */
+#define ORACLE_ORDER_DEVICE16 2 /* 16 lanes per row: rows of <= 48 sixteen-byte chunks (scan_topk.cuh LPR) */
 
 int oracle_version(void) { return 1; }
 int oracle_max_threads(void) {
@@ -128,14 +129,15 @@ static float score_simd(int metric, const float* q, const float* y, int d) {
 }
 
 /* The B200 kernels' order: elements are grouped in chunks of `chunk` (4 for fp32 rows, 8 for bf16
- * rows); lane l of 32 owns chunks l, l+32, ... and accumulates them in ascending element order
- * with a fused multiply-add; lanes are then combined by the xor butterfly 16,8,4,2,1. */
-static float score_device(int metric, const float* q, const float* y, int d, int chunk) {
+ * rows); lane l of `lanes` owns chunks l, l+lanes, ... and accumulates them in ascending element order
+ * with a fused multiply-add; lanes are then combined by the xor butterfly lanes/2,...,1.  lanes is 32, or 16
+ * for rows of <= 48 chunks (<= 768 bytes), where the kernels put two rows on one warp. */
+static float score_device(int metric, const float* q, const float* y, int d, int chunk, int lanes) {
     float lane[32];
     for (int l = 0; l < 32; ++l) lane[l] = 0.0f;
     int nchunk = (d + chunk - 1) / chunk;
     for (int c = 0; c < nchunk; ++c) {
-        int l = c & 31;
+        int l = c % lanes;
         float a = lane[l];
         for (int e = c * chunk; e < (c + 1) * chunk && e < d; ++e) {
             if (metric == ORACLE_METRIC_IP) {
@@ -149,16 +151,18 @@ static float score_device(int metric, const float* q, const float* y, int d, int
     }
     /* padding elements (d not a multiple of chunk) contribute fmaf(0,0,a) = a (IP) or
      * fmaf(0-0,0-0,a) = a (L2): no effect, skipped above. */
-    for (int m = 16; m >= 1; m >>= 1) {
+    for (int m = lanes / 2; m >= 1; m >>= 1) {
         float t[32];
-        for (int l = 0; l < 32; ++l) t[l] = lane[l] + lane[l ^ m];
-        for (int l = 0; l < 32; ++l) lane[l] = t[l];
+        for (int l = 0; l < lanes; ++l) t[l] = lane[l] + lane[l ^ m];
+        for (int l = 0; l < lanes; ++l) lane[l] = t[l];
     }
     return lane[0];
 }
 
 static inline float score_one(int metric, int order, int chunk, const float* q, const float* y, int d) {
-    return order == ORACLE_ORDER_DEVICE ? score_device(metric, q, y, d, chunk) : score_simd(metric, q, y, d);
+    if (order == ORACLE_ORDER_DEVICE) return score_device(metric, q, y, d, chunk, 32);
+    if (order == ORACLE_ORDER_DEVICE16) return score_device(metric, q, y, d, chunk, 16);
+    return score_simd(metric, q, y, d);
 }
 
 void oracle_scores(int metric, int order, int chunk, const float* db, int64_t n, int d, const float* q,
@@ -360,7 +364,7 @@ void oracle_normalize_rows(float* x, int64_t n, int d, int order) {
 #pragma omp parallel for schedule(static)
     for (int64_t r = 0; r < n; ++r) {
         float* v = x + r * (int64_t)d;
-        float ss = order == ORACLE_ORDER_DEVICE ? score_device(ORACLE_METRIC_IP, v, v, d, 4)
+        float ss = order == ORACLE_ORDER_DEVICE ? score_device(ORACLE_METRIC_IP, v, v, d, 4, 32)
                                                 : score_simd(ORACLE_METRIC_IP, v, v, d);
         float nrm = sqrtf(ss);
         if ((double)nrm <= 1e-8) {

@@ -17,7 +17,15 @@ SRC = HERE / "flat_oracle.c"
 LIB = HERE / "_build" / "liboracle.so"
 
 METRIC_IP, METRIC_L2 = 0, 1
-ORDER_SIMD, ORDER_DEVICE = 0, 1
+ORDER_SIMD, ORDER_DEVICE, ORDER_DEVICE16 = 0, 1, 2
+
+
+def device_order(d: int, chunk: int) -> int:
+    """The order code of the kernels' arithmetic for rows of d elements stored in chunks of `chunk`
+    (4 = fp32 rows, 8 = bf16 rows): 16 lanes per row when the padded row has <= 48 sixteen-byte chunks
+    and their number is a multiple of 16 (csrc/cabi.cu: b200_index_create), else 32."""
+    nvec = -(-d // chunk)
+    return ORDER_DEVICE16 if (nvec <= 48 and nvec % 16 == 0) else ORDER_DEVICE
 
 _lib = None
 
@@ -99,6 +107,8 @@ def normalize_rows(x: np.ndarray, order: int = ORDER_SIMD) -> np.ndarray:
 def scores(metric: int, db: np.ndarray, q: np.ndarray, order: int = ORDER_SIMD, chunk: int = 4) -> np.ndarray:
     db, q = _f32(db), _f32(q).reshape(-1)
     out = np.empty(db.shape[0], dtype=np.float32)
+    if order == ORDER_DEVICE:
+        order = device_order(db.shape[1], chunk)
     lib().oracle_scores(metric, order, chunk, _pf(db), db.shape[0], db.shape[1], _pf(q), _pf(out))
     return out
 
@@ -123,6 +133,8 @@ def search(metric: int, db: np.ndarray, q: np.ndarray, k: int, ids: np.ndarray |
     if ids is not None:
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         idp = _pi(ids)
+    if order == ORDER_DEVICE:
+        order = device_order(d, chunk)
     fn = lib().oracle_search_rowpar if rowpar else lib().oracle_search
     rc = fn(metric, order, chunk, _pf(db), n, d, idp, _pf(q), nq, k, _pf(D), _pi(I))
     if rc:
