@@ -40,14 +40,30 @@ def nvcc_path() -> str:
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
-    sources = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "b200_flat.h"]
+    """Every csrc/*.cu is compiled to an object in parallel, then linked into the shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    cus = sorted(CSRC.glob("*.cu"))
+    sources = cus + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "b200_flat.h"]
     if not force and _newer(LIB, sources):
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", str(LIB)] + [str(s) for s in sorted(CSRC.glob("*.cu"))]
-    subprocess.run(cmd, check=True)
+    objdir = ROOT / "c99_vectordb_b200" / "build"
+    objdir.mkdir(exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared",)]
+    nvcc = nvcc_path()
+
+    def compile_one(cu: Path) -> Path:
+        obj = objdir / (cu.stem + ".o")
+        cmd = [nvcc, *compile_flags, "-c"]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        cmd += ["-o", str(obj), str(cu)]
+        subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(cus)) as pool:
+        objs = list(pool.map(compile_one, cus))
+    subprocess.run([nvcc, *NVCC_FLAGS, "-o", str(LIB)] + [str(o) for o in objs], check=True)
     return LIB
 
 

@@ -572,17 +572,14 @@ struct ScanPlan {
 
 typedef void (*ScanFn)(const ScanParams);
 #define SCAN_RB 4
-// 32 lanes per row: query blocks 1/2/4/8.  16 lanes per row (short rows): query blocks 1 and 8 only.
+// The scan kernel instantiations live in scan_bulk.cu / scan_ldg.cu (separate translation units so
+// the build parallelises): 32 lanes per row with query blocks 1/2/4/8, 16 lanes per row (short rows)
+// with query blocks 1 and 8.
+ScanFn b200_pick_scan_bulk(int metric, int store, int qb, int lpr);
+ScanFn b200_pick_scan_ldg(int metric, int store, int qb, int lpr);
 static ScanFn pick_scan(int metric, int store, int qb, int variant, int lpr) {
-#define SC(M, S, Q, V, L) \
-    if (metric == M && store == S && qb == Q && variant == V && lpr == L) return scan_topk_kernel<M, S, Q, SCAN_RB, V, L>;
-#define SC_Q(M, S, V) SC(M, S, 1, V, 32) SC(M, S, 2, V, 32) SC(M, S, 4, V, 32) SC(M, S, 8, V, 32) SC(M, S, 1, V, 16) SC(M, S, 8, V, 16)
-#define SC_S(M, V) SC_Q(M, 0, V) SC_Q(M, 1, V)
-    SC_S(0, B200_VARIANT_BULK) SC_S(1, B200_VARIANT_BULK) SC_S(0, B200_VARIANT_LDG) SC_S(1, B200_VARIANT_LDG)
-#undef SC_S
-#undef SC_Q
-#undef SC
-    return nullptr;
+    return variant == B200_VARIANT_BULK ? b200_pick_scan_bulk(metric, store, qb, lpr)
+                                        : b200_pick_scan_ldg(metric, store, qb, lpr);
 }
 
 typedef void (*MergeFn)(const ScanParams, uint32_t);
