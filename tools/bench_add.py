@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=2_000_000)
 ap.add_argument("--d", type=int, default=1024)
 ap.add_argument("--dev-n", type=int, default=10_000_000)
+ap.add_argument("--host-only", action="store_true")
 a = ap.parse_args()
 rng = np.random.default_rng(0)
 x = rng.standard_normal((a.n, a.d), dtype=np.float32)
@@ -32,6 +33,8 @@ for store in ("f32", "bf16"):
             idx.index.close()
         print(json.dumps({"what": "host-fed add_with_ids", "n": a.n, "d": a.d, "store": store, "normalize": normalize,
                           "seconds": round(best, 4), "rows_per_s": round(a.n / best), "host_GBps": round(a.n * a.d * 4 / best / 1e9, 2)}), flush=True)
+if a.host_only:
+    sys.exit(0)
 # device-fed: the rows are generated in HBM, then ingested by K1
 src = torch.empty((a.dev_n, a.d), dtype=torch.float32, device="cuda")
 _cabi.check(_cabi.load().b200_synth_rows_dev(src.data_ptr(), a.dev_n, a.d, 1234, 0, 0, C.c_void_p(1)))
