@@ -864,7 +864,7 @@ static int ensure_shadow(b200_index* ix, cudaStream_t st) {
         ix->sh_rows = nullptr;
         ix->sh_norm2 = nullptr;
         ix->sh_cap_rows = 0;
-        size_t cap = (size_t)std::max<int64_t>(ix->ntotal, ix->capacity);
+        size_t cap = (size_t)ix->ntotal;  // the rows present, not the reserved capacity: the shadow is rebuilt on change anyway
         cudaError_t e = cudaMalloc((void**)&ix->sh_rows, cap * kpad * sizeof(__nv_bfloat16));
         if (e == cudaSuccess) e = cudaMalloc((void**)&ix->sh_norm2, cap * sizeof(float));
         if (e != cudaSuccess) {
