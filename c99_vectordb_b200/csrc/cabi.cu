@@ -342,10 +342,13 @@ extern "C" int b200_index_get_option(b200_index* ix, const char* name, int64_t* 
 // add
 // ---------------------------------------------------------------------------------------------
 typedef void (*IngestFn)(const IngestParams);
-static IngestFn pick_ingest(int store, int normalize, int vec) {
-#define ING(S, N, V) \
-    if (store == S && normalize == N && vec == V) return ingest_rows_kernel<S, N, V>;
-    ING(0, 0, 0) ING(0, 0, 1) ING(0, 1, 0) ING(0, 1, 1) ING(1, 0, 0) ING(1, 0, 1) ING(1, 1, 0) ING(1, 1, 1)
+// regs: 0 = general two-pass form; 4 / 8 = whole row held in registers (d <= 512 / d <= 1024)
+static IngestFn pick_ingest(int store, int normalize, int vec, int regs) {
+#define ING(S, N, V, R) \
+    if (store == S && normalize == N && vec == V && regs == R) return ingest_rows_kernel<S, N, V, R>;
+#define ING_SN(S, N) ING(S, N, 0, 0) ING(S, N, 1, 0) ING(S, N, 1, 4) ING(S, N, 1, 8)
+    ING_SN(0, 0) ING_SN(0, 1) ING_SN(1, 0) ING_SN(1, 1)
+#undef ING_SN
 #undef ING
     return nullptr;
 }
@@ -361,7 +364,10 @@ static int ingest_dev(int d, int d_pad, int store, const float* src_dev, uint8_t
     p.d = d;
     p.d_pad = d_pad;
     int vec = (d % 4 == 0) && (((uintptr_t)src_dev & 15) == 0);
-    IngestFn fn = pick_ingest(store, normalize ? 1 : 0, vec);
+    int regs = 0;
+    if (vec && (dst_pitch & 15) == 0 && (((uintptr_t)dst) & 15) == 0 && (store == B200_STORE_BF16 ? d_pad % 8 == 0 : true))
+        regs = d <= 512 ? 4 : (d <= 1024 ? 8 : 0);
+    IngestFn fn = pick_ingest(store, normalize ? 1 : 0, vec, regs);
     int64_t blocks = std::min<int64_t>((n + 7) / 8, (int64_t)num_sms * 8);
     fn<<<(unsigned)std::max<int64_t>(1, blocks), 256, 0, st>>>(p);
     if (launches) ++*launches;

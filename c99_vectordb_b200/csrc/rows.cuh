@@ -17,7 +17,25 @@ struct IngestParams {
     int d_pad;             // destination elements per row (zero padded)
 };
 
-template <int STORE, int NORMALIZE, int VEC>
+template <int STORE>
+__device__ __forceinline__ void ingest_store4(uint8_t* dst, int c, const float (&v)[4]) {
+    if (STORE == 0) {
+        *reinterpret_cast<float4*>(dst + 16 * (size_t)c) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 w;
+        w.x = *reinterpret_cast<uint32_t*>(&a);
+        w.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(dst + 8 * (size_t)c) = w;
+    }
+}
+
+// REGS > 0: the row (d % 4 == 0, d <= 128 * REGS, 16-byte aligned source and destination) is loaded
+// ONCE into REGS float4 registers per lane, the norm is reduced, and the scaled row is stored from the
+// registers — one HBM read and one write per element, all of a lane's loads in flight together.
+// REGS == 0: general two-pass form (odd d, unaligned pointers, very long rows).
+template <int STORE, int NORMALIZE, int VEC, int REGS>
 __global__ void __launch_bounds__(256) ingest_rows_kernel(const IngestParams p) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -26,6 +44,44 @@ __global__ void __launch_bounds__(256) ingest_rows_kernel(const IngestParams p) 
     for (uint64_t row = warp_global; row < p.n; row += warps_total) {
         const float* src = p.src + row * (uint64_t)p.d;
         uint8_t* dst = p.dst + row * p.pitch_bytes;
+        if (REGS > 0) {
+            float4 v[REGS > 0 ? REGS : 1];
+#pragma unroll
+            for (int j = 0; j < REGS; ++j) {
+                const int c = lane + 32 * j;
+                v[j] = c < nchunk ? *reinterpret_cast<const float4*>(src + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float nrm = 1.0f;
+            bool zero = false;
+            if (NORMALIZE) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int j = 0; j < REGS; ++j) {  // same order as the two-pass form: chunks lane, lane+32, ...
+                    if (lane + 32 * j < nchunk) {
+                        acc = fmaf(v[j].x, v[j].x, acc);
+                        acc = fmaf(v[j].y, v[j].y, acc);
+                        acc = fmaf(v[j].z, v[j].z, acc);
+                        acc = fmaf(v[j].w, v[j].w, acc);
+                    }
+                }
+                acc = warp_sum_xor(acc);
+                nrm = __fsqrt_rn(acc);
+                zero = ((double)nrm <= 1e-8);
+            }
+#pragma unroll
+            for (int j = 0; j < REGS; ++j) {
+                const int c = lane + 32 * j;
+                if (c < (p.d_pad >> 2)) {
+                    float o[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                    if (NORMALIZE) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) o[e] = zero ? 0.0f : __fdiv_rn(o[e], nrm);
+                    }
+                    ingest_store4<STORE>(dst, c, o);
+                }
+            }
+            continue;
+        }
         float scale_den = 1.0f;
         bool zero = false;
         if (NORMALIZE) {
@@ -62,21 +118,12 @@ __global__ void __launch_bounds__(256) ingest_rows_kernel(const IngestParams p) 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] = zero ? 0.0f : __fdiv_rn(v[j], scale_den);
             }
-            if (STORE == 0) {
-                if ((p.pitch_bytes & 15) == 0) {
-                    *reinterpret_cast<float4*>(dst + 16 * (size_t)c) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {  // dense destination with d % 4 != 0 (normalised query scratch)
+            if (STORE == 0 && (p.pitch_bytes & 15) != 0) {  // dense destination with d % 4 != 0 (normalised query scratch)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (4 * c + j < p.d) reinterpret_cast<float*>(dst)[4 * c + j] = v[j];
-                }
+                for (int j = 0; j < 4; ++j)
+                    if (4 * c + j < p.d) reinterpret_cast<float*>(dst)[4 * c + j] = v[j];
             } else {
-                __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
-                __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
-                uint2 w;
-                w.x = *reinterpret_cast<uint32_t*>(&a);
-                w.y = *reinterpret_cast<uint32_t*>(&b);
-                *reinterpret_cast<uint2*>(dst + 8 * (size_t)c) = w;
+                ingest_store4<STORE>(dst, c, v);
             }
         }
     }
