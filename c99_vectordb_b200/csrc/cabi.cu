@@ -625,7 +625,7 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
     const bool auto_variant = variant == B200_SCAN_AUTO;
     if (auto_variant) variant = ix->pitch >= 512 ? B200_VARIANT_BULK : B200_VARIANT_LDG;
     if (variant == B200_VARIANT_BULK) {
-        int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_BULK / 32);
+        int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), (qb >= 4 ? 256 : B200_SCAN_THREADS_BULK) / 32);
         const int nw_min = auto_variant ? 3 : 1;
         bool ok = false;
         // Every warp owns `stages` tiles of tile_rows rows.  Prefer ~12 KB tiles, but shrink the tile

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256) final_merge_kernel(const ScanParams p, ui
 // full warp per row would leave lanes idle — the warp then works on SETS = 2 row sets of RB rows at once
 // (lanes 0-15 on the first, 16-31 on the second) and the butterfly has 4 rounds (8,4,2,1).
 template <int METRIC, int STORE, int QB, int RB, int VARIANT, int LPR>
-__global__ void __launch_bounds__(VARIANT == B200_VARIANT_BULK ? B200_SCAN_THREADS_BULK : B200_SCAN_THREADS_LDG,
+__global__ void __launch_bounds__(VARIANT == B200_VARIANT_BULK ? (QB >= 4 ? 256 : B200_SCAN_THREADS_BULK) : B200_SCAN_THREADS_LDG,
                                   VARIANT == B200_VARIANT_BULK ? 1 : (QB >= 4 ? 2 : 4))  // QB*RB accumulators need registers
 scan_topk_kernel(const ScanParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
