@@ -67,6 +67,7 @@ class ShardedIndexFlat:
         self.merge_launches = 0
         self._bufs = {}
         self._fused = False
+        self._host_stage = {}
 
     # ---- add --------------------------------------------------------------------------------
     def add_with_ids(self, x: np.ndarray, ids: np.ndarray) -> None:
@@ -196,18 +197,31 @@ class ShardedIndexFlat:
         return D, I
 
     def search(self, x: np.ndarray, k: int):
-        """Host query -> host result (every rank passes the same query and gets the same answer)."""
+        """Host query -> host result (every rank passes the same query and gets the same answer).
+        Pinned staging buffers are cached per shape; one stream synchronisation per call."""
         import torch
 
         x = np.ascontiguousarray(x, dtype=np.float32)
         assert x.ndim == 2 and x.shape[1] == self.d
-        if self.device.type == "cuda":
-            host = torch.from_numpy(x).pin_memory()
-            q = host.to(self.device, non_blocking=True)
-        else:
-            q = torch.from_numpy(x)
-        D, I = self.search_device(q, k)
-        return D.cpu().numpy(), I.cpu().numpy()
+        if self.device.type != "cuda":
+            D, I = self.search_device(torch.from_numpy(x), k)
+            return D.numpy().copy(), I.numpy().copy()
+        key = (x.shape[0], int(k))
+        st = self._host_stage.get(key)
+        if st is None:
+            st = (torch.empty((x.shape[0], self.d), dtype=torch.float32).pin_memory(),
+                  torch.empty((x.shape[0], self.d), dtype=torch.float32, device=self.device),
+                  torch.empty((x.shape[0], int(k)), dtype=torch.float32).pin_memory(),
+                  torch.empty((x.shape[0], int(k)), dtype=torch.int64).pin_memory())
+            self._host_stage[key] = st
+        hq, dq, hD, hI = st
+        hq.numpy()[...] = x
+        dq.copy_(hq, non_blocking=True)
+        D, I = self.search_device(dq, k)
+        hD.copy_(D, non_blocking=True)
+        hI.copy_(I, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return hD.numpy().copy(), hI.numpy().copy()
 
     # ---- pieces -----------------------------------------------------------------------------
     def _local_search(self, q, k, D_loc, I_loc) -> None:
