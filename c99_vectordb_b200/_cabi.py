@@ -32,6 +32,8 @@ SIGNATURES = [
     ("b200_index_get_option", C.c_int, [_h, C.c_char_p, _ip]),
     ("b200_index_add", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     ("b200_index_add_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    ("b200_index_add_file", C.c_int, [_h, C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    ("b200_index_write_file", C.c_int, [_h, C.c_char_p, C.c_int64, C.c_int64]),
     ("b200_index_add_synthetic", C.c_int, [_h, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int64]),
     ("b200_index_search", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     ("b200_index_search_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

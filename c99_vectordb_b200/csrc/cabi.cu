@@ -2,7 +2,13 @@
 // Single translation unit: nvcc -shared -gencode arch=compute_100a,code=sm_100a (see build.py).
 #include "../../include/b200_flat.h"
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
+#include <cerrno>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -400,12 +406,52 @@ static void parallel_memcpy(uint8_t* dst, const uint8_t* src, size_t bytes, int 
     for (auto& t : th) t.join();
 }
 
-template <typename Consume>
-static int upload_staged(b200_index* ix, const uint8_t* src, size_t bytes, uint8_t* dst_dev, bool dst_is_ring,
-                         size_t align, Consume consume) {
-    const size_t kChunk = (size_t)64 << 20;
-    size_t chunk = kChunk / align * align;
-    if (chunk == 0) chunk = align;
+// Threaded pread/pwrite of one contiguous file range (the page cache copy is the cost; 16 threads as for memcpy).
+static int parallel_file_io(int fd, uint8_t* buf, size_t bytes, int64_t file_off, int threads, bool write) {
+    std::atomic<int> bad{0};
+    auto work = [&bad, fd, buf, file_off, write](size_t off, size_t len) {
+        while (len > 0) {
+            ssize_t r = write ? pwrite(fd, buf + off, len, (off_t)(file_off + (int64_t)off))
+                              : pread(fd, buf + off, len, (off_t)(file_off + (int64_t)off));
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) {  // error, or end of file before the promised bytes
+                bad.store(r < 0 ? errno : -1);
+                return;
+            }
+            off += (size_t)r;
+            len -= (size_t)r;
+        }
+    };
+    if (threads <= 1 || bytes < ((size_t)4 << 20)) {
+        work(0, bytes);
+    } else {
+        std::vector<std::thread> th;
+        size_t per = (bytes + threads - 1) / threads;
+        per = (per + 4095) & ~(size_t)4095;
+        for (int t = 0; t < threads; ++t) {
+            size_t off = (size_t)t * per;
+            if (off >= bytes) break;
+            th.emplace_back(work, off, std::min(per, bytes - off));
+        }
+        for (auto& t : th) t.join();
+    }
+    int e = bad.load();
+    if (e == -1) return fail("read error: file ends before the bytes its header promises");
+    if (e != 0) return fail("%s: %s", write ? "pwrite" : "pread", strerror(e));
+    return 0;
+}
+
+static int staging_threads() {
+    unsigned hc = std::thread::hardware_concurrency();
+    int threads = (int)std::min<unsigned>(16, std::max<unsigned>(1, hc));  // host-memory bound: 16 threads measured best
+    if (const char* env = getenv("B200_UPLOAD_THREADS")) {
+        int t = atoi(env);
+        if (t >= 1 && t <= 64) threads = t;
+    }
+    return threads;
+}
+
+static int ensure_pinned_ring(b200_index* ix, size_t chunk) {
     if (!ix->up_pin[0] || ix->up_chunk < chunk) {
         for (int i = 0; i < 2; ++i) {
             if (ix->up_pin[i]) CK(cudaFreeHost(ix->up_pin[i]));
@@ -415,20 +461,37 @@ static int upload_staged(b200_index* ix, const uint8_t* src, size_t bytes, uint8
         }
         ix->up_chunk = chunk;
     }
-    unsigned hc = std::thread::hardware_concurrency();
-    int threads = (int)std::min<unsigned>(16, std::max<unsigned>(1, hc));  // host-memory bound: 16 threads measured best
-    if (const char* env = getenv("B200_UPLOAD_THREADS")) {
-        int t = atoi(env);
-        if (t >= 1 && t <= 64) threads = t;
+    return 0;
+}
+
+// Where the bytes of an upload come from: pageable host memory, or a byte range of an open file.
+struct HostSource {
+    const uint8_t* mem = nullptr;
+    int fd = -1;
+    int64_t file_off = 0;
+    int fill(uint8_t* pinned, size_t off, size_t len, int threads) const {
+        if (fd >= 0) return parallel_file_io(fd, pinned, len, file_off + (int64_t)off, threads, false);
+        parallel_memcpy(pinned, mem + off, len, threads);
+        return 0;
     }
+};
+
+template <typename Consume>
+static int upload_staged(b200_index* ix, const HostSource& src, size_t bytes, uint8_t* dst_dev, bool dst_is_ring,
+                         size_t align, Consume consume) {
+    const size_t kChunk = (size_t)64 << 20;
+    size_t chunk = kChunk / align * align;
+    if (chunk == 0) chunk = align;
+    CKI(ensure_pinned_ring(ix, chunk));
+    const int threads = staging_threads();
     cudaStream_t st = ix->stream;
     size_t off = 0;
     int b = 0;
-    bool used[2] = {false, false};
+    bool used[2] = {true, true};  // an earlier upload's DMA may still be reading the ring (never-recorded events return at once)
     while (off < bytes) {
         size_t len = std::min(chunk, bytes - off);
         if (used[b]) CK(cudaEventSynchronize(ix->up_ev[b]));  // the DMA that last read this buffer is done
-        parallel_memcpy(ix->up_pin[b], src + off, len, threads);
+        CKI(src.fill(ix->up_pin[b], off, len, threads));
         uint8_t* target = dst_is_ring ? dst_dev : dst_dev + off;
         CK(cudaMemcpyAsync(target, ix->up_pin[b], len, cudaMemcpyHostToDevice, st));
         CK(cudaEventRecord(ix->up_ev[b], st));
@@ -448,29 +511,41 @@ static int note_ids(b200_index* ix, bool explicit_ids) {
     return 0;
 }
 
+// x: host or device rows, or null when `file` names the source (rows at file->file_off; ids, if ids_file_off >= 0,
+// at that byte offset of the same file).
 static int add_common(b200_index* ix, const float* x, bool x_is_dev, int64_t n, const int64_t* ids,
-                      int normalize) {
+                      int normalize, const HostSource* file = nullptr, int64_t ids_file_off = -1) {
     if (!ix) return fail("null index");
     if (n < 0) return fail("negative n");
     if (n == 0) return 0;
-    if (!x) return fail("x is null");
+    if (!x && !file) return fail("x is null");
+    const bool with_ids = ids != nullptr || (file && ids_file_off >= 0);
     CKI(use_device(ix));
-    CKI(note_ids(ix, ids != nullptr));
-    CKI(ensure_capacity(ix, ix->ntotal + n, ids != nullptr));
+    CKI(note_ids(ix, with_ids));
+    CKI(ensure_capacity(ix, ix->ntotal + n, with_ids));
     cudaStream_t st = ix->stream;
     if (ids)
         CK(cudaMemcpyAsync(ix->ids + ix->ntotal, ids, (size_t)n * sizeof(int64_t),
                            x_is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    else if (with_ids) {
+        HostSource idsrc = *file;
+        idsrc.file_off = ids_file_off;
+        CKI(upload_staged(ix, idsrc, (size_t)n * sizeof(int64_t), (uint8_t*)(ix->ids + ix->ntotal), false, sizeof(int64_t),
+                          [](uint8_t*, size_t, size_t) { return 0; }));
+    }
     uint8_t* dst = ix->rows + (size_t)ix->ntotal * ix->pitch;
     const bool plain = (ix->store == B200_STORE_F32) && !normalize && (ix->d == ix->d_pad);
     const size_t row_bytes = (size_t)ix->d * 4;
-    const bool big_host = !x_is_dev && (size_t)n * row_bytes >= ((size_t)8 << 20);
-    if (plain && (x_is_dev || !big_host)) {
+    const bool big_host = file || (!x_is_dev && (size_t)n * row_bytes >= ((size_t)8 << 20));
+    HostSource src;
+    if (file) src = *file;
+    else src.mem = (const uint8_t*)x;
+    if (plain && !file && (x_is_dev || !big_host)) {
         CK(cudaMemcpyAsync(dst, x, (size_t)n * ix->pitch,
                            x_is_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     } else if (plain) {
         // fp32 rows stored verbatim: pinned ring straight into the resident rows
-        CKI(upload_staged(ix, (const uint8_t*)x, (size_t)n * row_bytes, dst, false, row_bytes,
+        CKI(upload_staged(ix, src, (size_t)n * row_bytes, dst, false, row_bytes,
                           [](uint8_t*, size_t, size_t) { return 0; }));
     } else if (x_is_dev) {
         CKI(ingest_dev(ix->d, ix->d_pad, ix->store, x, dst, ix->pitch, n, normalize, ix->num_sms, st, &ix->launches));
@@ -485,7 +560,7 @@ static int add_common(b200_index* ix, const float* x, bool x_is_dev, int64_t n, 
             ix->stage_cap = chunk_bytes;
         }
         if (big_host) {
-            CKI(upload_staged(ix, (const uint8_t*)x, (size_t)n * row_bytes, (uint8_t*)ix->stage, true, row_bytes,
+            CKI(upload_staged(ix, src, (size_t)n * row_bytes, (uint8_t*)ix->stage, true, row_bytes,
                               [&](uint8_t* dev_chunk, size_t off, size_t len) {
                                   int64_t r0 = (int64_t)(off / row_bytes), nr = (int64_t)(len / row_bytes);
                                   return ingest_dev(ix->d, ix->d_pad, ix->store, (const float*)dev_chunk,
@@ -510,6 +585,87 @@ extern "C" int b200_index_add(b200_index* ix, const float* x_host, int64_t n, co
 extern "C" int b200_index_add_dev(b200_index* ix, const float* x_dev, int64_t n, const int64_t* ids_dev,
                                   int normalize) {
     return add_common(ix, x_dev, true, n, ids_dev, normalize);
+}
+
+struct FdGuard {
+    int fd = -1;
+    ~FdGuard() {
+        if (fd >= 0) close(fd);
+    }
+};
+
+extern "C" int b200_index_add_file(b200_index* ix, const char* path, int64_t rows_offset, int64_t n,
+                                   int64_t ids_offset, int normalize) {
+    if (!ix || !path) return fail("null argument");
+    if (n < 0 || rows_offset < 0) return fail("bad file range");
+    if (n == 0) return 0;
+    FdGuard g;
+    g.fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (g.fd < 0) return fail("open %s: %s", path, strerror(errno));
+    struct stat sb;
+    if (fstat(g.fd, &sb) != 0) return fail("fstat %s: %s", path, strerror(errno));
+    const int64_t row_bytes = (int64_t)ix->d * 4;
+    if (rows_offset + n * row_bytes > (int64_t)sb.st_size || (ids_offset >= 0 && ids_offset + n * 8 > (int64_t)sb.st_size))
+        return fail("read error: %s is shorter than its header promises", path);
+    HostSource src;
+    src.fd = g.fd;
+    src.file_off = rows_offset;
+    return add_common(ix, nullptr, false, n, nullptr, normalize, &src, ids_offset);
+}
+
+// rows [0, ntotal) as dense fp32 at rows_offset, ids (int64) at ids_offset when >= 0; the file must exist.
+// Device -> pinned ring -> threaded pwrite; the D2H of chunk c+1 overlaps the file write of chunk c.
+extern "C" int b200_index_write_file(b200_index* ix, const char* path, int64_t rows_offset, int64_t ids_offset) {
+    if (!ix || !path) return fail("null argument");
+    if (rows_offset < 0) return fail("bad file offset");
+    if (ix->ntotal == 0) return 0;
+    CKI(use_device(ix));
+    FdGuard g;
+    g.fd = open(path, O_WRONLY | O_CLOEXEC);
+    if (g.fd < 0) return fail("open %s: %s", path, strerror(errno));
+    const int threads = staging_threads();
+    cudaStream_t st = ix->stream;
+    CK(cudaStreamSynchronize(st));
+    const size_t row_bytes = (size_t)ix->d * 4;
+    if (ix->store != B200_STORE_F32) {
+        // bf16 rows widen to fp32 on the host (lossless); not a hot path
+        const int64_t step = std::max<int64_t>(1, (int64_t)(((size_t)64 << 20) / row_bytes));
+        std::vector<float> tmp((size_t)std::min<int64_t>(step, ix->ntotal) * ix->d);
+        for (int64_t r0 = 0; r0 < ix->ntotal; r0 += step) {
+            int64_t nr = std::min<int64_t>(step, ix->ntotal - r0);
+            CKI(b200_index_get_rows(ix, r0, nr, tmp.data()));
+            CKI(parallel_file_io(g.fd, (uint8_t*)tmp.data(), (size_t)nr * row_bytes, rows_offset + r0 * (int64_t)row_bytes, threads, true));
+        }
+    } else {
+        size_t chunk_rows = std::max<size_t>(1, ((size_t)64 << 20) / row_bytes);
+        CKI(ensure_pinned_ring(ix, chunk_rows * row_bytes));
+        chunk_rows = ix->up_chunk / row_bytes;
+        int64_t pending_r0 = -1, pending_n = 0;
+        int pending_b = 0, b = 0;
+        for (int64_t r0 = 0; r0 < ix->ntotal || pending_r0 >= 0; r0 += (int64_t)chunk_rows) {
+            int64_t nr = r0 < ix->ntotal ? std::min<int64_t>((int64_t)chunk_rows, ix->ntotal - r0) : 0;
+            if (nr > 0) {
+                CK(cudaMemcpy2DAsync(ix->up_pin[b], row_bytes, ix->rows + (size_t)r0 * ix->pitch, ix->pitch, row_bytes,
+                                     (size_t)nr, cudaMemcpyDeviceToHost, st));
+                CK(cudaEventRecord(ix->up_ev[b], st));
+            }
+            if (pending_r0 >= 0) {
+                CK(cudaEventSynchronize(ix->up_ev[pending_b]));
+                CKI(parallel_file_io(g.fd, ix->up_pin[pending_b], (size_t)pending_n * row_bytes,
+                                     rows_offset + pending_r0 * (int64_t)row_bytes, threads, true));
+            }
+            pending_r0 = nr > 0 ? r0 : -1;
+            pending_n = nr;
+            pending_b = b;
+            b ^= 1;
+        }
+    }
+    if (ids_offset >= 0) {
+        std::vector<int64_t> ids((size_t)ix->ntotal);
+        CKI(b200_index_get_ids(ix, ids.data()));
+        CKI(parallel_file_io(g.fd, (uint8_t*)ids.data(), ids.size() * 8, ids_offset, threads, true));
+    }
+    return 0;
 }
 
 extern "C" int b200_synth_rows_dev(float* out_dev, int64_t n, int d, uint64_t seed, int64_t first_row,

@@ -356,50 +356,60 @@ def _read_exact(f, n: int) -> bytes:
     return b
 
 
-def _write_flat(f, idx: IndexFlat) -> None:
+def _write_flat_header(f, idx: IndexFlat) -> int:
+    """Flat index header up to and including the payload length; returns the payload's byte offset."""
     f.write(b"IxFI" if idx.metric_type == METRIC_INNER_PRODUCT else b"IxF2")
     n = idx.ntotal
     _write_header(f, idx, n)
     f.write(struct.pack("<Q", n * idx.d))  # code bytes / 4
-    step = max(1, (64 << 20) // (idx.d * 4))
-    for i0 in range(0, n, step):
-        idx.reconstruct_n(i0, min(step, n - i0)).tofile(f)
+    return f.tell()
 
 
 def write_index(index: Index, path: str) -> None:
-    """faiss.write_index (memo_cli.py:361, :448).  bf16-stored rows are widened to fp32 (lossless)."""
+    """faiss.write_index (memo_cli.py:361, :448).  bf16-stored rows are widened to fp32 (lossless).
+    Headers are written here; the rows and ids go device -> pinned ring -> file inside
+    b200_index_write_file (no intermediate numpy copies)."""
+    path = os.fspath(path)
+    if isinstance(index, IndexIDMap):
+        base, with_ids = index.index, True
+    elif isinstance(index, IndexFlat):
+        base, with_ids = index, False
+    else:
+        raise RuntimeError(f"don't know how to serialize {type(index).__name__}")
+    n = base.ntotal
     with open(path, "wb") as f:
-        if isinstance(index, IndexIDMap):
+        if with_ids:
             f.write(index._fourcc)
-            _write_header(f, index, index.ntotal)
-            _write_flat(f, index.index)
-            ids = index.index._ids()
-            f.write(struct.pack("<Q", ids.shape[0]))
-            ids.tofile(f)
-        elif isinstance(index, IndexFlat):
-            _write_flat(f, index)
-        else:
-            raise RuntimeError(f"don't know how to serialize {type(index).__name__}")
+            _write_header(f, index, n)
+        rows_off = _write_flat_header(f, base)
+        ids_off = -1
+        if with_ids:
+            f.seek(rows_off + n * base.d * 4)
+            f.write(struct.pack("<Q", n))
+            ids_off = f.tell()
+    if n:
+        _cabi.check(_cabi.load().b200_index_write_file(base._h, path.encode(), rows_off, ids_off))
 
 
-def _read_any(f, device):
+def _read_any(f, path: str, device):
     fourcc = _read_exact(f, 4)
     if fourcc in (b"IxMp", b"IxM2"):
         d, ntotal, metric = _read_header(f)
         # the nested flat payload must be added together with the ids that follow it
-        base, rows = _read_flat_payload(f, device)
+        base, rows_off, n = _read_flat_payload(f, device)
+        f.seek(rows_off + n * base.d * 4)
         n_ids, = struct.unpack("<Q", _read_exact(f, 8))
-        if n_ids != rows.shape[0]:
+        if n_ids != n:
             raise RuntimeError("id_map size does not match the nested index")
-        ids = np.frombuffer(_read_exact(f, 8 * n_ids), dtype="<i8").astype(np.int64)
+        ids_off = f.tell()
         wrapper = (IndexIDMap2 if fourcc == b"IxM2" else IndexIDMap)(base)
-        if n_ids:
-            wrapper.add_with_ids(rows, ids)
+        if n:
+            _cabi.check(_cabi.load().b200_index_add_file(base._h, path.encode(), rows_off, n, ids_off, 0))
         return wrapper
     f.seek(-4, os.SEEK_CUR)
-    base, rows = _read_flat_payload(f, device)
-    if rows.shape[0]:
-        base.add(rows)
+    base, rows_off, n = _read_flat_payload(f, device)
+    if n:
+        _cabi.check(_cabi.load().b200_index_add_file(base._h, path.encode(), rows_off, n, -1, 0))
     return base
 
 
@@ -441,13 +451,13 @@ def _read_flat_payload(f, device):
     count, = struct.unpack("<Q", _read_exact(f, 8))
     if count != ntotal * d:
         raise RuntimeError("flat payload size does not match header")
-    rows = np.frombuffer(_read_exact(f, 4 * count), dtype="<f4").astype(np.float32).reshape(ntotal, d)
     base = IndexFlat(d, metric, device=device)
-    return base, rows
+    return base, f.tell(), ntotal
 
 
 def read_index(path: str, device: int | None = None) -> Index:
     """faiss.read_index (memo_cli.py:255): raises on a missing or corrupt file (memo catches
     Exception and starts a fresh index, :256-257)."""
+    path = os.fspath(path)
     with open(path, "rb") as f:
-        return _read_any(f, device)
+        return _read_any(f, path, device)

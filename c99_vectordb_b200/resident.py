@@ -277,6 +277,11 @@ def make_server(socket_path: str, backend="c99_vectordb_b200.index", max_residen
 
 def serve(socket_path: str, backend="c99_vectordb_b200.index", max_resident: int = 8, idle_seconds: float = 0.0) -> None:
     srv = make_server(socket_path, backend, max_resident)
+    try:  # pay device start-up now, not inside the first client's read_index
+        warm = srv.service.backend.IndexFlat(8, METRIC_L2)
+        getattr(warm, "close", lambda: None)()
+    except Exception as ex:  # no device: keep serving, every compute request will fail loudly
+        print(f"[b200 resident] device warm-up failed: {ex}", file=sys.stderr)
     if idle_seconds > 0:
         def reaper():
             while not srv.service.stopping:

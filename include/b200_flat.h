@@ -88,6 +88,18 @@ int b200_index_add(b200_index* ix, const float* x_host, int64_t n, const int64_t
                    int normalize);
 int b200_index_add_dev(b200_index* ix, const float* x_dev, int64_t n, const int64_t* ids_dev,
                        int normalize);
+/* ---- .memo payload I/O (fast load / save) -------------------------------------------------
+ * replaces: the bulk byte movement inside faiss.read_index(path), memo_cli.py:255, and
+ *           faiss.write_index(index, path), memo_cli.py:361 and :448.  The host side parses / writes
+ *           the small faiss headers; these move the payload without intermediate host copies:
+ * add_file:   n dense float32 rows at byte rows_offset of `path` (and n int64 ids at ids_offset, or
+ *             ids_offset < 0 for none) go file -> pinned ring (threaded pread) -> device (-> K1).
+ *             A file shorter than rows_offset + n*d*4 (or the id range) is an error, nothing is added.
+ * write_file: rows [0, ntotal) as dense float32 at rows_offset (bf16 rows widened, lossless) and the
+ *             ids at ids_offset (>= 0) of an EXISTING file: device -> pinned ring -> threaded pwrite. */
+int b200_index_add_file(b200_index* ix, const char* path, int64_t rows_offset, int64_t n,
+                        int64_t ids_offset, int normalize);
+int b200_index_write_file(b200_index* ix, const char* path, int64_t rows_offset, int64_t ids_offset);
 /* synthetic rows generated on the device by the counter-based generator of DESIGN.md §6
  * (bit-identical to oracle/flat_oracle.c:oracle_synth_rows); rows get ids first_id + i when
  * with_ids != 0.  Used by bench.py / tests for databases too large to upload. */
