@@ -70,6 +70,8 @@ int b200_index_reserve(b200_index* ix, int64_t n_total);
  *   scan_query_block (1|2|4|8), scan_dynamic_tiles (-1 auto|0|1), scan_claim_chunk, scan_fused_tail
  *   fullrank_min_k        k at or above which the full-ranking (radix sort) path is used (default 257)
  *   normalize_queries     1: L2-normalise queries on the device before searching (cosine)
+ *   host_staged_results   1 (default): results of 32 MB or more (memo's k = ntotal) and query blocks of 4 MB or more
+ *                         cross PCIe through the pinned ring with threaded host copies; 0: plain copies
  *   gemm_min_nq           batched tensor-core path (K3) for nq >= this (default 2; 0 disables)
  *   gemm_min_rows, gemm_emit_factor, gemm_sample_tiles, gemm_chunk_tiles, gemm_cta_group (1|2)
  * Read-only statistics of the last search (b200_index_get_option): stat_gemm_used,

@@ -254,3 +254,45 @@ def test_reference_adapter_runs_unmodified_over_the_service(service, tmp_path, m
     assert [r.doc_id for r in got] == [r.doc_id for r in ref]
     assert [r.score for r in got] == [r.score for r in ref]
     sys.modules.pop("memo_cli", None)
+
+
+def test_concurrent_clients_are_serialised_correctly(service, tmp_path):
+    """Several CLI processes at once: each connection has its own handle table, requests are
+    serialised by the service lock, nobody sees another client's rows."""
+    d = 16
+    path = tmp_path / "shared.memo"
+    shared = resident.IndexIDMap2(resident.IndexFlatL2(d))
+    xs = _rows(400, d, 40)
+    shared.add_with_ids(xs, np.arange(400, dtype=np.int64))
+    resident.write_index(shared, str(path))
+    ref = stub.IndexIDMap2(stub.IndexFlat(d, stub.METRIC_L2))
+    ref.add_with_ids(xs, np.arange(400, dtype=np.int64))
+    errors = []
+
+    def worker(seed):
+        try:
+            c = resident.ResidentClient(service.sock, autostart=False)
+            info, _ = c.call("open", {"path": str(path)})
+            mine, _ = c.call("create", {"d": d, "metric": 1, "idmap": True})
+            own = _rows(20 + seed, d, 100 + seed)
+            c.call("add", {"h": mine["h"], "with_ids": True}, (own, np.arange(20 + seed, dtype=np.int64) + 1000 * seed))
+            for it in range(25):
+                q = _rows(2, d, 1000 * seed + it)
+                _, (D, I) = c.call("search", {"h": info["h"], "k": 5}, (q,))
+                Dr, Ir = ref.search(q, 5)
+                assert np.array_equal(I, Ir) and np.array_equal(D, Dr)
+                _, (D2, I2) = c.call("search", {"h": mine["h"], "k": 3}, (q,))
+                assert ((I2 >= 1000 * seed) & (I2 < 1000 * seed + 20 + seed)).all()
+            assert c.call("ntotal", {"h": mine["h"]})[0]["ntotal"] == 20 + seed
+            c.close()
+        except Exception as ex:  # surfaced in the main thread
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(1, 7)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    st = service.stats()
+    assert st["loads"] == 0 and st["hits"] == 6
