@@ -1,0 +1,151 @@
+"""Parity at BASELINE.json's FULL sizes through size-independent properties (the CPU oracle cannot
+scan 30-150 GB in seconds, so it checks what it can reach exactly):
+
+* every returned (row, distance) is recomputed by the oracle from the counter-based generator
+  (same row, same summation order) and must be BIT-EXACT;
+* the list is best-first under the stated tie rule, ids are unique and in range;
+* top-1 / top-10 / top-100 are prefixes of one another;
+* completeness on a sample: the oracle scores several 64k-row blocks at random offsets (and the blocks
+  around planted rows); no sampled row may beat the k-th result without being in the result;
+* planted queries (a database row itself) come back first (L2: distance exactly 0);
+* merge linearity: searching two half databases and merging the two lists with the oracle's merge
+  equals searching the whole (what the multi-GPU path relies on);
+* the tensor-core batched path (K3) returns the same ids and distances as the scan path (K2).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+DB_SEED, Q_SEED = 1234, 5678
+
+
+@pytest.fixture(scope="module")
+def b200(gpu):
+    import c99_vectordb_b200 as m
+
+    return m
+
+
+def host_rows(first_row, n, d, normalize, store):
+    """Rows [first_row, first_row+n) exactly as the device holds them (K1 normalise, bf16 rounding)."""
+    x = oracle.synth_rows(n, d, DB_SEED, first_row=first_row)
+    if normalize:
+        x = oracle.normalize_rows(x, oracle.ORDER_DEVICE)
+    if store == "bf16":
+        x = oracle.round_bf16(x)
+    return x
+
+
+def better(metric, s_a, r_a, s_b, r_b):
+    """(score, row) a strictly before b under the tie rule."""
+    if s_a != s_b:
+        return s_a > s_b if metric == 0 else s_a < s_b
+    return r_a < r_b
+
+
+def check_list(metric, D, I, n):
+    valid = I >= 0
+    assert valid.all() and (I < n).all()
+    assert len(set(I.tolist())) == len(I)
+    for j in range(1, len(I)):
+        assert not better(metric, D[j], I[j], D[j - 1], I[j - 1]), f"position {j} out of order"
+
+
+CASES = [
+    # BASELINE headline / config 2 database, config 3, config 4
+    pytest.param(dict(n=10_000_000, d=768, metric=0, store="f32", normalize=False, halves=True, k3=True), id="10Mx768_ip_f32"),
+    pytest.param(dict(n=100_000_000, d=384, metric=1, store="f32", normalize=False, halves=False, k3=False), id="100Mx384_l2_f32"),
+    pytest.param(dict(n=10_000_000, d=1024, metric=0, store="bf16", normalize=True, halves=True, k3=False), id="10Mx1024_cos_bf16"),
+]
+
+
+@pytest.mark.parametrize("c", CASES)
+def test_full_size_properties(b200, c):
+    n, d, metric, store, norm = c["n"], c["d"], c["metric"], c["store"], c["normalize"]
+    chunk = 8 if store == "bf16" else 4
+    idx = b200.IndexFlat(d, metric, store=store, normalize=norm)
+    try:
+        idx.add_synthetic(n, DB_SEED)
+    except RuntimeError as e:  # a smaller device than the 180 GB B200 cannot hold config 3
+        if "allocate" in str(e):
+            pytest.skip(str(e))
+        raise
+    assert idx.ntotal == n
+    rng = np.random.default_rng(99)
+    planted = sorted(int(r) for r in rng.integers(0, n, size=3)) + [0, n - 1]
+    q = np.concatenate([oracle.synth_rows(3, d, Q_SEED)] + [host_rows(r, 1, d, norm, "f32") for r in planted])
+    qn = oracle.normalize_rows(q, oracle.ORDER_DEVICE) if norm else q  # what the device scores against
+    nq = q.shape[0]
+
+    D1, I1 = idx.search(q[:1], 1)  # single-query latency path, k = 1
+    D10 = np.empty((nq, 10), np.float32)
+    I10 = np.empty((nq, 10), np.int64)
+    for i in range(nq):  # one query at a time = the headline call
+        D10[i], I10[i] = (a[0] for a in idx.search(q[i:i + 1], 10))
+    D100, I100 = idx.search(q[:1], 100)
+    assert I1[0, 0] == I10[0, 0] and D1[0, 0] == D10[0, 0]
+    np.testing.assert_array_equal(I100[0, :10], I10[0])
+    np.testing.assert_array_equal(D100[0, :10], D10[0])
+
+    for i in range(nq):
+        check_list(metric, D10[i], I10[i], n)
+        # bit-exact distances: the oracle recomputes each returned row from the generator
+        for j in range(10):
+            row = host_rows(int(I10[i, j]), 1, d, norm, store)
+            s = oracle.scores(metric, row, qn[i], order=oracle.ORDER_DEVICE, chunk=chunk)[0]
+            assert s == D10[i, j], (i, j, int(I10[i, j]), float(s), float(D10[i, j]))
+    check_list(metric, D100[0], I100[0], n)
+
+    # planted rows come back first
+    for t, r in enumerate(planted):
+        i = 3 + t
+        if metric == 1:
+            assert I10[i, 0] == r and D10[i, 0] == 0.0
+        elif norm:
+            assert I10[i, 0] == r and abs(D10[i, 0] - 1.0) < 1e-2
+
+    # completeness on a sample of blocks
+    B = 65536
+    offsets = [int(o) for o in rng.integers(0, n - B, size=5)] + [0, n - B] + [max(0, min(n - B, r - B // 2)) for r in planted[:2]]
+    for off in offsets:
+        blk = host_rows(off, B, d, norm, store)
+        for i in (0, 1, 3):
+            s = oracle.scores(metric, blk, qn[i], order=oracle.ORDER_DEVICE, chunk=chunk)
+            kth_s, kth_r = D10[i, 9], int(I10[i, 9])
+            cand = np.nonzero(s >= kth_s)[0] if metric == 0 else np.nonzero(s <= kth_s)[0]
+            for jrow in cand:
+                r = off + int(jrow)
+                if better(metric, s[jrow], r, kth_s, kth_r):
+                    assert r in I10[i].tolist(), f"row {r} (score {s[jrow]}) beats the 10th result but was not returned"
+
+    # the batched tensor-core path agrees with the scan path
+    if c["k3"]:
+        qb = oracle.synth_rows(40, d, Q_SEED + 7)
+        Dk3, Ik3 = idx.search(qb, 100)
+        assert idx.get_option("stat_gemm_used") == 1
+        idx.set_option("gemm_min_nq", 0)
+        Dk2, Ik2 = idx.search(qb[:8], 100)
+        idx.set_option("gemm_min_nq", 2)
+        np.testing.assert_array_equal(Ik3[:8], Ik2)
+        np.testing.assert_array_equal(Dk3[:8], Dk2)
+        for i in range(40):
+            check_list(metric, Dk3[i], Ik3[i], n)
+
+    # merge linearity over two half databases (ids = global row positions)
+    if c["halves"]:
+        h = n // 2
+        parts_D, parts_I = [], []
+        for lo, cnt in ((0, h), (h, n - h)):
+            half = b200.IndexIDMap2(b200.IndexFlat(d, metric, store=store, normalize=norm))
+            half.index.add_synthetic(cnt, DB_SEED, first_row=lo, with_ids=True, first_id=lo)
+            Dh, Ih = half.search(q[:4], 10)
+            parts_D.append(Dh)
+            parts_I.append(Ih)
+            del half
+        Dm, Im = oracle.merge_topk(metric, np.stack(parts_D), np.stack(parts_I))
+        np.testing.assert_array_equal(Im, I10[:4])
+        np.testing.assert_array_equal(Dm, D10[:4])
+    idx.close()
