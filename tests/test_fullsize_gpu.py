@@ -149,3 +149,32 @@ def test_full_size_properties(b200, c):
         np.testing.assert_array_equal(Im, I10[:4])
         np.testing.assert_array_equal(Dm, D10[:4])
     idx.close()
+
+
+def test_config2_full_batch(b200):
+    """BASELINE config 2 at full size: 10,000 queries x 10M x 768, k = 100 through the tensor-core path;
+    order / uniqueness for every query, and 16 sampled queries equal the exact scan bit for bit."""
+    n, d, nq, k = 10_000_000, 768, 10_000, 100
+    idx = b200.IndexFlat(d, 0)
+    idx.add_synthetic(n, DB_SEED)
+    Q = oracle.synth_rows(nq, d, Q_SEED)
+    D, I = idx.search(Q, k)
+    assert idx.get_option("stat_gemm_used") == 1
+    assert (I >= 0).all() and (I < n).all()
+    assert (np.diff(D, axis=1) <= 0).all()                      # IP: descending
+    ties = np.diff(D, axis=1) == 0
+    assert (np.diff(I, axis=1)[ties] > 0).all()                 # equal scores: smaller row first
+    Is = np.sort(I, axis=1)
+    assert (np.diff(Is, axis=1) > 0).all()                      # no row twice
+    pick = np.random.default_rng(5).choice(nq, size=16, replace=False)
+    idx.set_option("gemm_min_nq", 0)
+    D2, I2 = idx.search(Q[pick], k)
+    assert idx.get_option("stat_gemm_used") == 0
+    np.testing.assert_array_equal(I[pick], I2)
+    np.testing.assert_array_equal(D[pick], D2)
+    # and the oracle recomputes a few returned distances from the generator
+    for qi in pick[:4]:
+        for j in (0, 49, 99):
+            row = host_rows(int(I[qi, j]), 1, d, False, "f32")
+            assert oracle.scores(0, row, Q[qi], order=oracle.ORDER_DEVICE, chunk=4)[0] == D[qi, j]
+    idx.close()
