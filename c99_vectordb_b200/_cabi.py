@@ -39,6 +39,7 @@ SIGNATURES = [
     ("b200_index_search_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("b200_index_search_masked", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("b200_index_search_masked_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("b200_index_search_ids_allowed", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     ("b200_ipc_alloc", C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_char_p]),
     ("b200_ipc_open", C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     ("b200_ipc_close", C.c_int, [C.c_void_p]),

@@ -123,6 +123,13 @@ struct b200_index {
     const uint32_t* cur_mask = nullptr;  // row bitmap of the search in flight (device), or null
     uint32_t* mask_dev = nullptr;        // staging for host masks
     size_t mask_cap = 0;
+    int64_t* allow_dev = nullptr;        // allowed-id list of a search by ids (device copy)
+    size_t allow_cap = 0;
+    uint32_t* idbits_dev = nullptr;      // bitmap over the id range
+    size_t idbits_cap = 0;               // words
+    long long* ids_minmax_dev = nullptr; // [min, max] of the id map
+    int64_t ids_min = 0, ids_max = -1;
+    int64_t ids_minmax_rows = -1;        // ntotal the cached range was computed for (-1 = stale)
     int64_t launches = 0;
 };
 
@@ -224,6 +231,9 @@ extern "C" int b200_index_destroy(b200_index* ix) {
     }
     cudaFree(ix->xchg_peers_dev);
     cudaFree(ix->mask_dev);
+    cudaFree(ix->allow_dev);
+    cudaFree(ix->idbits_dev);
+    cudaFree(ix->ids_minmax_dev);
     cudaFree(ix->sh_rows);
     cudaFree(ix->sh_norm2);
     cudaFree(ix->sh_maxnorm);
@@ -250,6 +260,7 @@ extern "C" int b200_index_reset(b200_index* ix) {
     ix->ntotal = 0;
     ix->ids_state = 0;
     ix->sh_valid_rows = -1;
+    ix->ids_minmax_rows = -1;
     return 0;
 }
 
@@ -1482,6 +1493,75 @@ extern "C" int b200_index_search_masked(b200_index* ix, const float* q_host, int
         CKI(grow(&ix->mask_dev, &ix->mask_cap, words));
     }
     CK(cudaMemcpyAsync(ix->mask_dev, mask_host, words * 4, cudaMemcpyHostToDevice, ix->stream));
+    ix->cur_mask = ix->mask_dev;
+    int rc = b200_index_search(ix, q_host, nq, k, D_host, I_host);
+    ix->cur_mask = nullptr;
+    return rc;
+}
+
+
+extern "C" int b200_index_search_ids_allowed(b200_index* ix, const float* q_host, int64_t nq, int64_t k,
+                                             const int64_t* allowed_host, int64_t m, float* D_host, int64_t* I_host) {
+    if (!ix) return fail("null index");
+    if (m < 0 || (m > 0 && !allowed_host)) return fail("bad allowed-id list");
+    if (ix->ntotal == 0) return b200_index_search(ix, q_host, nq, k, D_host, I_host);
+    CKI(use_device(ix));
+    cudaStream_t st = ix->stream;
+    const uint64_t n = (uint64_t)ix->ntotal;
+    const size_t words = (size_t)((n + 31) / 32);
+    if (ix->mask_cap < words || ix->allow_cap < (size_t)m) CK(cudaStreamSynchronize(st));
+    CKI(grow(&ix->mask_dev, &ix->mask_cap, words));
+    CKI(grow(&ix->allow_dev, &ix->allow_cap, (size_t)std::max<int64_t>(m, 1)));
+    const unsigned blocks = (unsigned)ix->num_sms * 8;
+    const bool have_ids = ix->ids_state == 1;
+    if (m == 0) {
+        CK(cudaMemsetAsync(ix->mask_dev, 0, words * 4, st));
+    } else if (!have_ids) {
+        // ids are row positions: the row bitmap IS the id bitmap
+        CK(cudaMemcpyAsync(ix->allow_dev, allowed_host, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(ix->mask_dev, 0, words * 4, st));
+        scatter_allowed_kernel<<<blocks, 256, 0, st>>>(ix->allow_dev, (uint64_t)m, 0, n, ix->mask_dev);
+        ++ix->launches;
+        CK(cudaGetLastError());
+    } else {
+        if (ix->ids_minmax_rows != ix->ntotal) {  // id range of the map, cached until the next add / reset
+            if (!ix->ids_minmax_dev) CK(cudaMalloc((void**)&ix->ids_minmax_dev, 2 * sizeof(long long)));
+            const long long init[2] = {LLONG_MAX, LLONG_MIN};
+            long long got[2];
+            CK(cudaMemcpyAsync(ix->ids_minmax_dev, init, sizeof init, cudaMemcpyHostToDevice, st));
+            ids_minmax_kernel<<<blocks, 256, 0, st>>>(ix->ids, n, ix->ids_minmax_dev);
+            ++ix->launches;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(got, ix->ids_minmax_dev, sizeof got, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            ix->ids_min = got[0];
+            ix->ids_max = got[1];
+            ix->ids_minmax_rows = ix->ntotal;
+        }
+        const unsigned __int128 span = (unsigned __int128)((__int128)ix->ids_max - (__int128)ix->ids_min) + 1;
+        const uint64_t dense_limit = 64 * n + ((uint64_t)1 << 24);  // id bitmap of at most 8 N + 2 MB bytes
+        if (span <= dense_limit) {
+            const uint64_t range = (uint64_t)span;
+            const size_t bwords = (size_t)((range + 31) / 32);
+            if (ix->idbits_cap < bwords) CK(cudaStreamSynchronize(st));
+            CKI(grow(&ix->idbits_dev, &ix->idbits_cap, bwords));
+            CK(cudaMemcpyAsync(ix->allow_dev, allowed_host, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(ix->idbits_dev, 0, bwords * 4, st));
+            scatter_allowed_kernel<<<blocks, 256, 0, st>>>(ix->allow_dev, (uint64_t)m, ix->ids_min, range, ix->idbits_dev);
+            gather_row_mask_kernel<<<blocks, 256, 0, st>>>(ix->ids, n, ix->ids_min, range, ix->idbits_dev, ix->mask_dev);
+            ix->launches += 2;
+            CK(cudaGetLastError());
+        } else {
+            // sparse id space: sorted list + one binary search per row
+            std::vector<int64_t> sorted(allowed_host, allowed_host + m);
+            std::sort(sorted.begin(), sorted.end());
+            CK(cudaMemcpyAsync(ix->allow_dev, sorted.data(), (size_t)m * 8, cudaMemcpyHostToDevice, st));
+            gather_row_mask_sorted_kernel<<<blocks, 256, 0, st>>>(ix->ids, n, ix->allow_dev, (uint64_t)m, ix->mask_dev);
+            ++ix->launches;
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(st));  // `sorted` is pageable memory that dies with this scope
+        }
+    }
     ix->cur_mask = ix->mask_dev;
     int rc = b200_index_search(ix, q_host, nq, k, D_host, I_host);
     ix->cur_mask = nullptr;

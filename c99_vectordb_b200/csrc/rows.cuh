@@ -6,6 +6,7 @@
 // the 4-element chunks l, l+32, ... and sums squares in ascending element order with fmaf, then a
 // 16/8/4/2/1 xor butterfly (oracle/flat_oracle.c: oracle_normalize_device_order).
 #pragma once
+#include <climits>
 #include "common.cuh"
 
 struct IngestParams {
@@ -145,4 +146,87 @@ __global__ void __launch_bounds__(256) iota_ids_kernel(int64_t* out, uint64_t n,
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = first + (int64_t)i;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// id filter -> row bitmap (filtered search by record id).  The allowed ids are
+// scattered into a bitmap over the ID range [base, base + range) (one atomicOr each), then every
+// row looks its own id up in it and one ballot per 32 rows writes the row bitmap word the scan
+// kernels test.  Sparse id spaces use the sorted-list form (binary search per row).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ids_minmax_kernel(const int64_t* __restrict__ ids, uint64_t n, long long* out) {
+    long long lo = LLONG_MAX, hi = LLONG_MIN;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        long long v = ids[i];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+    for (int o = 16; o; o >>= 1) {
+        long long a = __shfl_xor_sync(0xffffffffu, lo, o), b = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+    }
+}
+
+__global__ void __launch_bounds__(256) scatter_allowed_kernel(const int64_t* __restrict__ allowed, uint64_t m, int64_t base,
+                                                              uint64_t range, uint32_t* __restrict__ bits) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const int64_t id = allowed[i];
+        if (id < base) continue;
+        const uint64_t off = (uint64_t)id - (uint64_t)base;
+        if (off < range) atomicOr(&bits[off >> 5], 1u << (off & 31));
+    }
+}
+
+// one thread per row, one ballot per warp = one row-bitmap word
+__global__ void __launch_bounds__(256) gather_row_mask_kernel(const int64_t* __restrict__ ids, uint64_t n, int64_t base,
+                                                              uint64_t range, const uint32_t* __restrict__ bits,
+                                                              uint32_t* __restrict__ row_mask) {
+    const uint64_t words = (n + 31) / 32;
+    const uint64_t wstride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < words; w += wstride) {
+        const uint64_t r = w * 32 + lane;
+        bool ok = false;
+        if (r < n) {
+            const int64_t id = ids[r];
+            if (id >= base) {
+                const uint64_t off = (uint64_t)id - (uint64_t)base;
+                ok = off < range && ((bits[off >> 5] >> (off & 31)) & 1u);
+            }
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) row_mask[w] = word;
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_row_mask_sorted_kernel(const int64_t* __restrict__ ids, uint64_t n,
+                                                                     const int64_t* __restrict__ sorted, uint64_t m,
+                                                                     uint32_t* __restrict__ row_mask) {
+    const uint64_t words = (n + 31) / 32;
+    const uint64_t wstride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < words; w += wstride) {
+        const uint64_t r = w * 32 + lane;
+        bool ok = false;
+        if (r < n) {
+            const int64_t id = ids[r];
+            uint64_t lo = 0, hi = m;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi) >> 1;
+                if (sorted[mid] < id) lo = mid + 1;
+                else hi = mid;
+            }
+            ok = lo < m && sorted[lo] == id;
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) row_mask[w] = word;
+    }
 }

@@ -180,16 +180,27 @@ class IndexFlat(Index):
         _cabi.check(_cabi.load().b200_index_add_synthetic(self._h, int(n), int(seed), int(first_row),
                                                           int(self.normalize), int(with_ids), int(first_id)))
 
-    def search(self, x, k: int, row_mask=None):
-        """faiss Index.search.  `row_mask` (extension, SURVEY.md 8f-1): bool array over row positions;
-        only rows whose entry is True can be returned — the filter runs inside the scan kernel."""
+    def search(self, x, k: int, row_mask=None, ids_allowed=None):
+        """faiss Index.search.  Extensions, the filter runs inside the search kernels:
+        `row_mask` — bool array over row positions, only rows whose entry is True can be returned;
+        `ids_allowed` — iterable of ids that may be returned (the row bitmap is built on the device)."""
         x = self._coerce_x(x)
         k = int(k)
         assert k > 0
         nq = x.shape[0]
         D = np.empty((nq, k), dtype=np.float32)
         I = np.empty((nq, k), dtype=np.int64)
-        if row_mask is None:
+        if ids_allowed is not None:
+            if row_mask is not None:
+                raise ValueError("give row_mask or ids_allowed, not both")
+            if isinstance(ids_allowed, np.ndarray):
+                allowed = np.ascontiguousarray(ids_allowed, dtype=np.int64).reshape(-1)
+            else:
+                allowed = np.fromiter((int(i) for i in ids_allowed), dtype=np.int64)
+            _cabi.check(_cabi.load().b200_index_search_ids_allowed(
+                self._h, x.ctypes.data, nq, k, allowed.ctypes.data if allowed.size else None, allowed.size,
+                D.ctypes.data, I.ctypes.data))
+        elif row_mask is None:
             _cabi.check(_cabi.load().b200_index_search(self._h, x.ctypes.data, nq, k, D.ctypes.data, I.ctypes.data))
         else:
             bits = pack_row_mask(row_mask, self.ntotal)
@@ -287,10 +298,7 @@ class IndexIDMap(Index):
 
     def search(self, x, k: int, row_mask=None, ids_allowed=None):
         """`ids_allowed` (extension): iterable of record ids that may be returned (filter push-down)."""
-        if ids_allowed is not None:
-            allowed = np.fromiter((int(i) for i in ids_allowed), dtype=np.int64)
-            row_mask = np.isin(self.index._ids(), allowed)
-        return self.index.search(x, k, row_mask=row_mask)
+        return self.index.search(x, k, row_mask=row_mask, ids_allowed=ids_allowed)
 
     def search_device(self, q, k: int, **kw):
         return self.index.search_device(q, k, **kw)

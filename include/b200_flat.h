@@ -131,6 +131,13 @@ int b200_index_search_masked(b200_index* ix, const float* q_host, int64_t nq, in
                              const uint32_t* mask_host, float* D_host, int64_t* I_host);
 int b200_index_search_masked_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k,
                                  const uint32_t* mask_dev, float* D_dev, int64_t* I_dev, void* stream);
+/* the same filter given as a list of m allowed RECORD IDS (any order, duplicates and unknown ids are
+ * fine; m = 0 allows nothing): the row bitmap is built on the device — ids scattered into a bitmap over
+ * the id range, one lookup per row (dense id spaces such as memo's record positions, memo_cli.py:276),
+ * or a sorted list + binary search per row (sparse ids) — and the masked search runs on it.  Replaces
+ * the O(ntotal) Python post-filter loop of memo_cli.py:491-521 without any per-row host work. */
+int b200_index_search_ids_allowed(b200_index* ix, const float* q_host, int64_t nq, int64_t k,
+                                  const int64_t* allowed_host, int64_t m, float* D_host, int64_t* I_host);
 /* ---- fused multi-GPU exchange (one process per GPU) --------------------------------------------
  * Instead of an NCCL all-gather + merge kernel, the scan kernel's last CTA stores its local top-k
  * into every rank's exchange buffer over NVLink peer mappings, flags it, waits for the peers and

@@ -458,3 +458,44 @@ def test_read_index_imports_memo_hnsw_files(b200, tmp_path):
     p.write_bytes(blob[:200])
     with pytest.raises(Exception):
         b200.read_index(str(p))
+
+
+@pytest.mark.parametrize("id_kind", ["dense", "sparse", "negative", "none"])
+def test_search_by_allowed_ids_builds_the_mask_on_the_device(b200, id_kind):
+    """ids_allowed (record ids, any order, duplicates, unknown ids) == an unfiltered search over exactly
+    the allowed rows; dense id spaces go through the id bitmap, sparse ones through the sorted list."""
+    n, d = 20011, 64
+    db, q = oracle.synth_rows(n, d, 31), oracle.synth_rows(3, d, 32)
+    rng = np.random.default_rng(7)
+    ids = {"dense": np.arange(n, dtype=np.int64) * 3 + 11,
+           "sparse": rng.permutation(n).astype(np.int64) * 1_000_003_000 + 5,
+           "negative": np.arange(n, dtype=np.int64) * 2 - n,
+           "none": None}[id_kind]
+    idx = make_index(b200, 1, d, db, ids)
+    label = ids if ids is not None else np.arange(n, dtype=np.int64)
+    for frac in (0.3, 0.002):
+        rows = np.nonzero(rng.random(n) < frac)[0]
+        allowed = np.concatenate([label[rows], label[rows[:5]], [2**62, -2**62, label.max() + 1]])  # dups + unknown
+        rng.shuffle(allowed)
+        for k in (1, 10, 300):
+            D, I = idx.search(q, k, ids_allowed=allowed)
+            Dw, Iw = oracle.search(1, db[rows], q, k, ids=label[rows], order=oracle.ORDER_DEVICE)
+            np.testing.assert_array_equal(I, Iw)
+            np.testing.assert_array_equal(D, Dw)
+    D, I = idx.search(q, 4, ids_allowed=[])            # nothing allowed
+    assert (I == -1).all()
+    D, I = idx.search(q, 4, ids_allowed=iter([int(label[7])]))
+    assert I[:, 0].tolist() == [int(label[7])] * 3 and (I[:, 1:] == -1).all()
+    # the cached id range follows adds and resets
+    if ids is not None:
+        extra = oracle.synth_rows(2, d, 33)
+        new_ids = np.array([label.max() + 10**15, label.min() - 10**15], dtype=np.int64)
+        idx.add_with_ids(extra, new_ids)
+        D, I = idx.search(extra, 1, ids_allowed=new_ids)
+        assert I[:, 0].tolist() == new_ids.tolist() and (D[:, 0] == 0).all()
+        idx.reset()
+        idx.add_with_ids(db[:50], np.arange(50, dtype=np.int64))
+        D, I = idx.search(q, 50, ids_allowed=[3, 4])
+        assert sorted(I[0][I[0] >= 0].tolist()) == [3, 4]
+    with pytest.raises(ValueError):
+        idx.search(q, 1, row_mask=np.ones(idx.ntotal, bool), ids_allowed=[1])
