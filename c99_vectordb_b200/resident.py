@@ -451,7 +451,8 @@ class Index:
         assert k > 0
         arrays = [self._coerce_x(x)]
         if ids_allowed is not None:
-            arrays.append(np.fromiter((int(i) for i in ids_allowed), dtype=np.int64))
+            arrays.append(np.ascontiguousarray(ids_allowed, dtype=np.int64).reshape(-1) if isinstance(ids_allowed, np.ndarray)
+                          else np.fromiter((int(i) for i in ids_allowed), dtype=np.int64))
         _, (D, I) = c.call("search", {"h": h, "k": k, "ids_allowed": ids_allowed is not None}, arrays)
         return D, I
 
