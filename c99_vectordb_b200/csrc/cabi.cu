@@ -59,7 +59,7 @@ static int fail(const char* fmt, ...) {
 struct b200_index {
     int d = 0, d_pad = 0, metric = 0, store = 0, device = 0;
     size_t pitch = 0;  // bytes per stored row
-    int lpr = 32;      // lanes sharing a row in the scan arithmetic: 16 for rows of <= 48 sixteen-byte chunks
+    int lpr = 32;      // lanes sharing a row in the scan arithmetic: 8 / 16 for short rows (see b200_index_create)
     uint8_t* rows = nullptr;
     int64_t ntotal = 0, capacity = 0;
     int64_t* ids = nullptr;
@@ -194,7 +194,9 @@ extern "C" int b200_index_create(b200_index** out, int d, int metric, int store,
     ix->pitch = (size_t)ix->d_pad * (store == B200_STORE_F32 ? 4 : 2);
     {
         const size_t nvec = ix->pitch / 16;
-        ix->lpr = (nvec <= 48 && nvec % 16 == 0) ? 16 : 32;  // part of the index's numerics: fixed at creation
+        // part of the index's numerics, fixed at creation: 8 lanes per row for rows of 8 or 16 sixteen-byte chunks
+        // (<= 256 B), 16 lanes for rows of <= 48 chunks in whole 16-chunk groups, else the full warp
+        ix->lpr = (nvec <= 16 && nvec % 8 == 0) ? 8 : (nvec <= 48 && nvec % 16 == 0) ? 16 : 32;
     }
     ix->num_sms = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
@@ -822,10 +824,11 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
     // the TMA-staged ring with dynamic tiles and as many warps as fit (<= 16) x 2 stages.  Short rows
     // and bf16 rows carry more instructions per byte and want the extra warps (bf16 d=1024: 1.09-1.12
     // of the measured peak vs 1.02 for direct loads); long rows still win with 3-4 warps (d=2048: 1.12
-    // vs 1.03).  Rows under 512 bytes go to the direct-load variant with its 32 resident warps/SM
-    // (d=64 fp32: 0.89 vs 0.86).
+    // vs 1.03).  Rows of 128 / 256 bytes use 8 lanes per row and the ring as well (r1_sweep14_*: d=64 fp32 1.10,
+    // d=32 fp32 1.09, bf16 d=64 1.07, bf16 d=128 0.99-1.05 vs 0.82-1.00 for direct loads); other rows under 512
+    // bytes go to the direct-load variant with its 32 resident warps/SM.
     const bool auto_variant = variant == B200_SCAN_AUTO;
-    if (auto_variant) variant = ix->pitch >= 512 ? B200_VARIANT_BULK : B200_VARIANT_LDG;
+    if (auto_variant) variant = (ix->pitch >= 512 || ix->lpr == 8) ? B200_VARIANT_BULK : B200_VARIANT_LDG;
     if (variant == B200_VARIANT_BULK) {
         int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), (qb >= 4 ? 256 : B200_SCAN_THREADS_BULK) / 32);
         const int nw_min = auto_variant ? 3 : 1;

@@ -13,8 +13,8 @@
 //                  the ncu evidence.
 //
 // Both produce bit-identical scores: lane l of the LPR lanes sharing a row accumulates 16-byte chunks
-// l, l+LPR, ... in ascending element order with fmaf, then an xor butterfly LPR/2 ... 1 (LPR = 32, or 16
-// for rows of <= 48 chunks; oracle/flat_oracle.c: score_device restates exactly this order).
+// l, l+LPR, ... in ascending element order with fmaf, then an xor butterfly LPR/2 ... 1 (LPR = 32, 16
+// for rows of <= 48 chunks, 8 for rows of 8 / 16 chunks; oracle/flat_oracle.c: score_device restates exactly this order).
 //
 // Top-k: per warp an unsorted k-entry list of 64-bit keys in shared memory plus the running
 // threshold tau = worst key kept; a row is inserted only when its key beats tau (rare after
@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(256) final_merge_kernel(const ScanParams p, ui
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
-// LPR = lanes that share one row: 32 normally; 16 for rows of <= 48 sixteen-byte chunks (<= 768 B), where a
+// LPR = lanes that share one row: 32 normally; 16 for rows of <= 48 sixteen-byte chunks (<= 768 B) and 8 for rows of
+// 8 / 16 chunks (128 / 256 B; SETS = 4 row sets, butterfly 4,2,1), where a
 // full warp per row would leave lanes idle — the warp then works on SETS = 2 row sets of RB rows at once
 // (lanes 0-15 on the first, 16-31 on the second) and the butterfly has 4 rounds (8,4,2,1).
 template <int METRIC, int STORE, int QB, int RB, int VARIANT, int LPR>

@@ -53,6 +53,7 @@
 #define ORACLE_ORDER_SIMD 0
 #define ORACLE_ORDER_DEVICE 1   /* 32 lanes per row */
 #define ORACLE_ORDER_DEVICE16 2 /* 16 lanes per row: rows of <= 48 sixteen-byte chunks (scan_topk.cuh LPR) */
+#define ORACLE_ORDER_DEVICE8 3  /* 8 lanes per row: rows of 8 or 16 sixteen-byte chunks */
 
 int oracle_version(void) { return 1; }
 int oracle_max_threads(void) {
@@ -162,6 +163,7 @@ static float score_device(int metric, const float* q, const float* y, int d, int
 static inline float score_one(int metric, int order, int chunk, const float* q, const float* y, int d) {
     if (order == ORACLE_ORDER_DEVICE) return score_device(metric, q, y, d, chunk, 32);
     if (order == ORACLE_ORDER_DEVICE16) return score_device(metric, q, y, d, chunk, 16);
+    if (order == ORACLE_ORDER_DEVICE8) return score_device(metric, q, y, d, chunk, 8);
     return score_simd(metric, q, y, d);
 }
 

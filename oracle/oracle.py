@@ -17,14 +17,16 @@ SRC = HERE / "flat_oracle.c"
 LIB = HERE / "_build" / "liboracle.so"
 
 METRIC_IP, METRIC_L2 = 0, 1
-ORDER_SIMD, ORDER_DEVICE, ORDER_DEVICE16 = 0, 1, 2
+ORDER_SIMD, ORDER_DEVICE, ORDER_DEVICE16, ORDER_DEVICE8 = 0, 1, 2, 3
 
 
 def device_order(d: int, chunk: int) -> int:
     """The order code of the kernels' arithmetic for rows of d elements stored in chunks of `chunk`
-    (4 = fp32 rows, 8 = bf16 rows): 16 lanes per row when the padded row has <= 48 sixteen-byte chunks
-    and their number is a multiple of 16 (csrc/cabi.cu: b200_index_create), else 32."""
+    (4 = fp32 rows, 8 = bf16 rows): 8 lanes per row when the padded row has 8 or 16 sixteen-byte chunks,
+    16 lanes when it has <= 48 chunks in whole groups of 16 (csrc/cabi.cu: b200_index_create), else 32."""
     nvec = -(-d // chunk)
+    if nvec <= 16 and nvec % 8 == 0:
+        return ORDER_DEVICE8
     return ORDER_DEVICE16 if (nvec <= 48 and nvec % 16 == 0) else ORDER_DEVICE
 
 _lib = None
