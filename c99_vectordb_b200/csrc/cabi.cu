@@ -169,6 +169,23 @@ extern "C" int b200_device_count(int* out_count) {
     return 0;
 }
 
+// Lanes of a warp that share one row in the scan arithmetic (scan_topk.cuh LPR), from the row length in 16-byte
+// chunks.  Whole groups keep their measured choices (8 lanes for 8 / 16 chunks, 16 lanes up to 48 chunks, else the
+// full warp); ragged rows of up to 64 chunks (1 KB) take the lane count that wastes the fewest chunk slots, ties
+// going to fewer lanes (d = 48 fp32: 12 of 32 lanes busy with a full warp, 12 of 16 slots with 8 lanes).
+// oracle/oracle.py: device_lanes restates this rule.
+static int pick_lpr(size_t nvec) {
+    if (nvec <= 16 && nvec % 8 == 0) return 8;
+    if (nvec <= 48 && nvec % 16 == 0) return 16;
+    if (nvec % 32 == 0 || nvec > 64) return 32;
+    int best = 32;
+    size_t best_slots = (nvec + 31) / 32 * 32;
+    const size_t s16 = (nvec + 15) / 16 * 16, s8 = (nvec + 7) / 8 * 8;
+    if (s16 <= best_slots) best = 16, best_slots = s16;
+    if (s8 <= best_slots) best = 8, best_slots = s8;
+    return best;
+}
+
 extern "C" int b200_index_create(b200_index** out, int d, int metric, int store, int device) {
     if (!out) return fail("out is null");
     *out = nullptr;
@@ -192,12 +209,7 @@ extern "C" int b200_index_create(b200_index** out, int d, int metric, int store,
     ix->device = device;
     ix->d_pad = store == B200_STORE_F32 ? (d + 3) / 4 * 4 : (d + 7) / 8 * 8;
     ix->pitch = (size_t)ix->d_pad * (store == B200_STORE_F32 ? 4 : 2);
-    {
-        const size_t nvec = ix->pitch / 16;
-        // part of the index's numerics, fixed at creation: 8 lanes per row for rows of 8 or 16 sixteen-byte chunks
-        // (<= 256 B), 16 lanes for rows of <= 48 chunks in whole 16-chunk groups, else the full warp
-        ix->lpr = (nvec <= 16 && nvec % 8 == 0) ? 8 : (nvec <= 48 && nvec % 16 == 0) ? 16 : 32;
-    }
+    ix->lpr = pick_lpr(ix->pitch / 16);  // part of the index's numerics: fixed at creation
     ix->num_sms = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);

@@ -20,14 +20,27 @@ METRIC_IP, METRIC_L2 = 0, 1
 ORDER_SIMD, ORDER_DEVICE, ORDER_DEVICE16, ORDER_DEVICE8 = 0, 1, 2, 3
 
 
-def device_order(d: int, chunk: int) -> int:
-    """The order code of the kernels' arithmetic for rows of d elements stored in chunks of `chunk`
-    (4 = fp32 rows, 8 = bf16 rows): 8 lanes per row when the padded row has 8 or 16 sixteen-byte chunks,
-    16 lanes when it has <= 48 chunks in whole groups of 16 (csrc/cabi.cu: b200_index_create), else 32."""
+def device_lanes(d: int, chunk: int) -> int:
+    """Lanes sharing a row in the kernels' arithmetic for rows of d elements stored in chunks of `chunk`
+    (4 = fp32 rows, 8 = bf16 rows) — the rule of csrc/cabi.cu: pick_lpr restated."""
     nvec = -(-d // chunk)
     if nvec <= 16 and nvec % 8 == 0:
-        return ORDER_DEVICE8
-    return ORDER_DEVICE16 if (nvec <= 48 and nvec % 16 == 0) else ORDER_DEVICE
+        return 8
+    if nvec <= 48 and nvec % 16 == 0:
+        return 16
+    if nvec % 32 == 0 or nvec > 64:
+        return 32
+    best, best_slots = 32, -(-nvec // 32) * 32
+    for lanes in (16, 8):
+        slots = -(-nvec // lanes) * lanes
+        if slots <= best_slots:
+            best, best_slots = lanes, slots
+    return best
+
+
+def device_order(d: int, chunk: int) -> int:
+    """The order code of that arithmetic."""
+    return {32: ORDER_DEVICE, 16: ORDER_DEVICE16, 8: ORDER_DEVICE8}[device_lanes(d, chunk)]
 
 _lib = None
 
