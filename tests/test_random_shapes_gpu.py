@@ -22,7 +22,7 @@ def b200(gpu):
 @pytest.mark.parametrize("seed", range(CASES))
 def test_random_case(b200, seed):
     rng = np.random.default_rng(1000 + seed)
-    d = int(rng.choice([1, 2, 3, 5, 8, 17, 31, 64, 100, 129, 384, 500, 768, 1000, 1024, 1536]))
+    d = int(rng.choice([1, 2, 3, 5, 8, 17, 31, 32, 48, 64, 96, 100, 129, 200, 260, 300, 384, 500, 768, 1000, 1024, 1536]))
     n = int(rng.integers(1, 6000)) if rng.random() < 0.7 else int(rng.integers(6000, 60000))
     nq = int(rng.choice([1, 1, 1, 2, 3, 4, 7, 8, 9, 16, 19]))
     k = int(rng.choice([1, 2, 5, 10, 33, 100, 256, 257, 1000]))
