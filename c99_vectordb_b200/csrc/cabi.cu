@@ -987,6 +987,38 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     return 0;
 }
 
+// Full ranking of a SMALL database (memo-sized: n <= 4096 rows; at 10k rows the single-CTA sort already loses to the radix passes) in one launch: one CTA per query builds the 64-bit
+// (score key, row) keys in shared memory, sorts them with the CTA bitonic network and emits the first k —
+// instead of the 14 launches of the radix path (memo's k = ntotal call at 1k rows: ~100 us -> one scan + one sort).
+// The 64-bit keys carry the tie rule, so the order equals the stable radix sort's.
+#define FULLRANK_SMALL_MAX 4096
+template <int METRIC>
+__global__ void __launch_bounds__(1024) fullrank_small_kernel(const uint32_t* __restrict__ hi_keys, uint32_t n, uint32_t m,
+                                                              int64_t k, const int64_t* __restrict__ id_map,
+                                                              float* __restrict__ D, int64_t* __restrict__ I) {
+    extern __shared__ uint64_t fr_keys[];
+    const uint32_t* hi = hi_keys + (size_t)blockIdx.x * n;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+        uint32_t h = i < n ? hi[i] : 0u;
+        fr_keys[i] = h ? (((uint64_t)h << 32) | (uint64_t)(0xFFFFFFFFu - i)) : 0ull;
+    }
+    cta_bitonic_sort_desc(fr_keys, m);
+    float* Dq = D + (size_t)blockIdx.x * k;
+    int64_t* Iq = I + (size_t)blockIdx.x * k;
+    for (int64_t i = threadIdx.x; i < k; i += blockDim.x) {
+        const uint64_t key = i < (int64_t)m ? fr_keys[i] : 0ull;
+        float dist = (METRIC == 0) ? -FLT_MAX : FLT_MAX;
+        int64_t id = -1;
+        if (key != 0ull) {
+            dist = b200_key_score(key, METRIC);
+            const uint32_t row = b200_key_row(key);
+            id = id_map ? id_map[row] : (int64_t)row;
+        }
+        Dq[i] = dist;
+        Iq[i] = id;
+    }
+}
+
 static int fullrank_one(b200_index* ix, const uint32_t* hi_keys, int64_t k, float* D, int64_t* I, cudaStream_t st) {
     const uint64_t n = (uint64_t)ix->ntotal;
     const uint32_t nblocks = (uint32_t)((n + RADIX_CHUNK - 1) / RADIX_CHUNK);
@@ -1407,9 +1439,26 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
         ScanPlan pl;
         CKI(plan_scan(ix, qb, 1, true, &pl));
         CKI(launch_scan(ix, pl, q_dev + (size_t)q0 * ix->d, nqb, 1, nullptr, nullptr, ix->fr_hi, st));
-        for (int qi = 0; qi < nqb; ++qi)
-            CKI(fullrank_one(ix, ix->fr_hi + (size_t)qi * n, k, D_dev + (size_t)(q0 + qi) * k,
-                             I_dev + (size_t)(q0 + qi) * k, st));
+        if (n <= FULLRANK_SMALL_MAX) {
+            const uint32_t m = std::max<uint32_t>(2, next_pow2((uint32_t)n));
+            const size_t fsmem = (size_t)m * 8;
+            const int64_t* idm = ix->ids_state == 1 ? ix->ids : nullptr;
+            if (ix->metric == B200_METRIC_IP) {
+                CK(cudaFuncSetAttribute(fullrank_small_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                fullrank_small_kernel<0><<<nqb, 1024, fsmem, st>>>(ix->fr_hi, (uint32_t)n, m, k, idm, D_dev + (size_t)q0 * k,
+                                                                   I_dev + (size_t)q0 * k);
+            } else {
+                CK(cudaFuncSetAttribute(fullrank_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                fullrank_small_kernel<1><<<nqb, 1024, fsmem, st>>>(ix->fr_hi, (uint32_t)n, m, k, idm, D_dev + (size_t)q0 * k,
+                                                                   I_dev + (size_t)q0 * k);
+            }
+            ++ix->launches;
+            CK(cudaGetLastError());
+        } else {
+            for (int qi = 0; qi < nqb; ++qi)
+                CKI(fullrank_one(ix, ix->fr_hi + (size_t)qi * n, k, D_dev + (size_t)(q0 + qi) * k,
+                                 I_dev + (size_t)(q0 + qi) * k, st));
+        }
         q0 += nqb;
     }
     return 0;

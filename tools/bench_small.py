@@ -8,7 +8,7 @@ import c99_vectordb_b200 as m
 from oracle import oracle
 
 d = 384
-for n in (1_000, 10_000, 100_000, 1_000_000):
+for n in (1_000, 4_000, 10_000, 100_000, 1_000_000):
     idx = m.IndexIDMap2(m.IndexHNSWFlat(d, 32))          # what memo's create_index builds: flat L2 behind the shim
     idx.index.add_synthetic(n, 1234, with_ids=True)
     q = oracle.synth_rows(1, d, 5678)
