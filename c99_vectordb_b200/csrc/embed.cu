@@ -8,7 +8,12 @@
 // CPython >= 3.11: vectors are reproducible across processes and bit-identical to the reference run
 // under PYTHONHASHSEED=0 (tests/golden/embed.npz).  Pure host code; no device work.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
+#include <thread>
+#include <vector>
 
 #include "../../include/b200_flat.h"
 
@@ -58,10 +63,8 @@ extern "C" int64_t b200_py_hash_seed0(const char* bytes, int64_t len) {
 
 // texts: n lower-cased UTF-8 strings concatenated in `utf8`, text i = [offsets[i], offsets[i+1]).
 // out: [n, dim] float32, un-normalised signed bucket counts (K1 normalises them at add time).
-extern "C" int b200_hash_embed(const char* utf8, const int64_t* offsets, int64_t n, int dim, float* out) {
-    if (!utf8 || !offsets || !out || n < 0 || dim <= 0) return 1;
-    const uint8_t* buf = reinterpret_cast<const uint8_t*>(utf8);
-    for (int64_t i = 0; i < n; ++i) {
+static void hash_embed_range(const uint8_t* buf, const int64_t* offsets, int64_t i0, int64_t i1, int dim, float* out) {
+    for (int64_t i = i0; i < i1; ++i) {
         float* v = out + (size_t)i * dim;
         for (int c = 0; c < dim; ++c) v[c] = 0.0f;
         int64_t p = offsets[i];
@@ -77,5 +80,33 @@ extern "C" int b200_hash_embed(const char* utf8, const int64_t* offsets, int64_t
             }
         }
     }
+}
+
+extern "C" int b200_hash_embed(const char* utf8, const int64_t* offsets, int64_t n, int dim, float* out) {
+    if (!utf8 || !offsets || !out || n < 0 || dim <= 0) return 1;
+    const uint8_t* buf = reinterpret_cast<const uint8_t*>(utf8);
+    // records are independent: split them over the host cores (a rebuild embeds every record, memo_cli.py:276-281)
+    unsigned hc = std::thread::hardware_concurrency();
+    int threads = (int)std::min<unsigned>(32, std::max<unsigned>(1, hc));
+    if (const char* env = getenv("B200_EMBED_THREADS")) {
+        int t = atoi(env);
+        if (t >= 1 && t <= 256) threads = t;
+    }
+    if (n < 2048 || threads == 1) {
+        hash_embed_range(buf, offsets, 0, n, dim, out);
+        return 0;
+    }
+    const int64_t bytes = offsets[n] - offsets[0];
+    std::vector<std::thread> th;
+    int64_t i0 = 0;
+    for (int t = 0; t < threads && i0 < n; ++t) {  // equal BYTES per thread, not equal record counts
+        const int64_t target = offsets[0] + bytes * (t + 1) / threads;
+        int64_t i1 = t + 1 == threads ? n : (int64_t)(std::upper_bound(offsets + i0, offsets + n, target) - offsets);
+        i1 = std::min<int64_t>(std::max<int64_t>(i1, i0), n);
+        if (i1 > i0) th.emplace_back(hash_embed_range, buf, offsets, i0, i1, dim, out);
+        i0 = i1;
+    }
+    if (i0 < n) hash_embed_range(buf, offsets, i0, n, dim, out);
+    for (auto& t : th) t.join();
     return 0;
 }

@@ -61,12 +61,21 @@ def embed_texts_stable(texts: Sequence[str], dim: int = DIM) -> np.ndarray:
     embed_text_hash buckets under PYTHONHASHSEED=0.  One C call instead of a Python token loop."""
     from . import _cabi
 
-    low = [t.lower().encode("utf-8") for t in texts]  # str.lower() stays in Python (Unicode case rules)
-    offsets = np.zeros(len(low) + 1, dtype=np.int64)
-    np.cumsum([len(b) for b in low], out=offsets[1:])
-    blob = b"".join(low)
-    out = np.empty((len(low), dim), dtype=np.float32)
-    rc = _cabi.load().b200_hash_embed(blob, offsets.ctypes.data, len(low), dim, out.ctypes.data)
+    n = len(texts)
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    joined = "\n".join(texts)
+    if joined.isascii():
+        # one lower() / encode() over everything: ASCII lower-casing keeps lengths, and the "\n" that ends up inside
+        # each record's byte range is not a token byte
+        blob = joined.lower().encode("ascii")
+        np.cumsum(np.fromiter(map(len, texts), dtype=np.int64, count=n) + 1, out=offsets[1:])
+        offsets[n] = len(blob)
+    else:
+        low = [t.lower().encode("utf-8") for t in texts]  # str.lower() stays in Python (Unicode case rules)
+        np.cumsum([len(b) for b in low], out=offsets[1:])
+        blob = b"".join(low)
+    out = np.empty((n, dim), dtype=np.float32)
+    rc = _cabi.load().b200_hash_embed(blob, offsets.ctypes.data, n, dim, out.ctypes.data)
     if rc:
         raise RuntimeError("b200_hash_embed failed")
     return out
