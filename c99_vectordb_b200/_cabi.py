@@ -16,6 +16,12 @@ METRIC_IP, METRIC_L2 = 0, 1
 STORE_F32, STORE_BF16 = 0, 1
 SCAN_AUTO, SCAN_BULK, SCAN_LDG = 0, 1, 2
 
+class MemoInfo(C.Structure):
+    """b200_memo_info (include/b200_flat.h)."""
+    _fields_ = [("kind", C.c_int32), ("d", C.c_int32), ("metric", C.c_int32), ("from_hnsw", C.c_int32),
+                ("ntotal", C.c_int64), ("rows_offset", C.c_int64), ("ids_offset", C.c_int64)]
+
+
 # every symbol include/b200_flat.h declares: (name, restype, argtypes)
 _fp = C.POINTER(C.c_float)
 _ip = C.POINTER(C.c_int64)
@@ -34,6 +40,10 @@ SIGNATURES = [
     ("b200_index_add_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     ("b200_index_add_file", C.c_int, [_h, C.c_char_p, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
     ("b200_index_write_file", C.c_int, [_h, C.c_char_p, C.c_int64, C.c_int64]),
+    ("b200_memo_probe", C.c_int, [C.c_char_p, C.POINTER(MemoInfo)]),
+    ("b200_memo_write_headers", C.c_int, [C.c_char_p, C.POINTER(MemoInfo), _ip, _ip]),
+    ("b200_index_save", C.c_int, [_h, C.c_char_p, C.c_int]),
+    ("b200_index_load", C.c_int, [C.POINTER(_h), C.c_char_p, C.c_int, C.c_int, C.POINTER(MemoInfo)]),
     ("b200_index_add_synthetic", C.c_int, [_h, C.c_int64, C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int64]),
     ("b200_index_search", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     ("b200_index_search_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

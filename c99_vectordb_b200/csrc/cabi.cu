@@ -728,6 +728,191 @@ extern "C" int b200_index_write_file(b200_index* ix, const char* path, int64_t r
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// whole .memo files: faiss index serialisation [upstream layout, SURVEY.md App. A.5]
+// header = int32 d, int64 ntotal, 2 x int64 (unused), uint8 is_trained, int32 metric (+ float32 metric_arg when > 1)
+// ---------------------------------------------------------------------------------------------
+struct FileGuard {
+    FILE* f = nullptr;
+    ~FileGuard() {
+        if (f) fclose(f);
+    }
+};
+
+static int rd(FILE* f, void* dst, size_t n) {
+    size_t got = fread(dst, 1, n, f);
+    if (got != n) return fail("read error: wanted %zu bytes, got %zu", n, got);
+    return 0;
+}
+
+static int rd_header(FILE* f, int32_t* d, int64_t* ntotal, int32_t* metric) {
+    int64_t dummy[2];
+    uint8_t trained;
+    CKI(rd(f, d, 4));
+    CKI(rd(f, ntotal, 8));
+    CKI(rd(f, dummy, 16));
+    CKI(rd(f, &trained, 1));
+    CKI(rd(f, metric, 4));
+    if (*metric > 1) {
+        float arg;
+        CKI(rd(f, &arg, 4));
+    }
+    if (*d <= 0 || *ntotal < 0) return fail("corrupt index header");
+    return 0;
+}
+
+// a serialised std::vector: uint64 count, then count elements; skipped, count returned
+static int skip_vector(FILE* f, size_t elem_bytes, uint64_t limit, uint64_t* count) {
+    uint64_t n = 0;
+    CKI(rd(f, &n, 8));
+    if (n > limit) return fail("implausible vector length in index file");
+    if (fseeko(f, (off_t)(n * elem_bytes), SEEK_CUR) != 0) return fail("seek failed: %s", strerror(errno));
+    *count = n;
+    return 0;
+}
+
+// IndexHNSWFlat: header, then the HNSW graph (assign_probas double[], cum_nneighbor_per_level int32[], levels int32[ntotal],
+// offsets size_t[ntotal+1], neighbors int32[], 5 x int32 scalars), then the flat storage index.  The graph is useless for
+// an exact flat index and is skipped [upstream write_HNSW layout, unverified here: every size is checked].
+static int skip_hnsw_graph(FILE* f, int64_t ntotal) {
+    const uint64_t big = (uint64_t)1 << 40;
+    uint64_t n = 0;
+    CKI(skip_vector(f, 8, 1u << 16, &n));
+    CKI(skip_vector(f, 4, 1u << 16, &n));
+    CKI(skip_vector(f, 4, big, &n));
+    if (n != (uint64_t)ntotal) return fail("HNSW levels do not match ntotal");
+    CKI(skip_vector(f, 8, big, &n));
+    if (n != (uint64_t)ntotal + 1) return fail("HNSW offsets do not match ntotal");
+    CKI(skip_vector(f, 4, big, &n));
+    uint8_t scalars[20];
+    return rd(f, scalars, sizeof scalars);
+}
+
+extern "C" int b200_memo_probe(const char* path, b200_memo_info* out) {
+    if (!path || !out) return fail("null argument");
+    memset(out, 0, sizeof *out);
+    out->ids_offset = -1;
+    FileGuard g;
+    g.f = fopen(path, "rb");
+    if (!g.f) return fail("could not open %s for reading: %s", path, strerror(errno));
+    struct stat sb;
+    if (fstat(fileno(g.f), &sb) != 0) return fail("fstat %s: %s", path, strerror(errno));
+    char cc[5] = {0, 0, 0, 0, 0};
+    CKI(rd(g.f, cc, 4));
+    int32_t d = 0, metric = 0;
+    int64_t ntotal = 0;
+    if (memcmp(cc, "IxMp", 4) == 0 || memcmp(cc, "IxM2", 4) == 0) {
+        out->kind = cc[3] == '2' ? 2 : 1;
+        CKI(rd_header(g.f, &d, &ntotal, &metric));  // the wrapper's own copy; the nested index decides
+        CKI(rd(g.f, cc, 4));
+    }
+    if (memcmp(cc, "IHNf", 4) == 0) {
+        CKI(rd_header(g.f, &d, &ntotal, &metric));
+        CKI(skip_hnsw_graph(g.f, ntotal));
+        out->from_hnsw = 1;
+        CKI(rd(g.f, cc, 4));  // the storage index
+    }
+    if (memcmp(cc, "IxFI", 4) != 0 && memcmp(cc, "IxF2", 4) != 0 && memcmp(cc, "IxFl", 4) != 0) {
+        for (int i = 0; i < 4; ++i)
+            if (cc[i] < 32 || cc[i] > 126) cc[i] = '?';
+        return fail("Index type '%s' not recognized", cc);
+    }
+    CKI(rd_header(g.f, &d, &ntotal, &metric));
+    uint64_t count = 0;
+    CKI(rd(g.f, &count, 8));
+    if (count != (uint64_t)ntotal * (uint64_t)d) return fail("flat payload size does not match header");
+    out->d = d;
+    out->metric = metric;
+    out->ntotal = ntotal;
+    out->rows_offset = (int64_t)ftello(g.f);
+    const int64_t rows_end = out->rows_offset + ntotal * (int64_t)d * 4;
+    if (rows_end > (int64_t)sb.st_size) return fail("read error: %s is shorter than its header promises", path);
+    if (out->kind) {
+        if (fseeko(g.f, (off_t)rows_end, SEEK_SET) != 0) return fail("seek failed: %s", strerror(errno));
+        uint64_t n_ids = 0;
+        CKI(rd(g.f, &n_ids, 8));
+        if (n_ids != (uint64_t)ntotal) return fail("id_map size does not match the nested index");
+        out->ids_offset = rows_end + 8;
+        if (out->ids_offset + ntotal * 8 > (int64_t)sb.st_size) return fail("read error: %s is shorter than its header promises", path);
+    }
+    return 0;
+}
+
+static int wr(FILE* f, const void* src, size_t n) {
+    if (fwrite(src, 1, n, f) != n) return fail("write error: %s", strerror(errno));
+    return 0;
+}
+static int wr_header(FILE* f, int32_t d, int64_t ntotal, int32_t metric) {
+    const int64_t dummy[2] = {1 << 20, 1 << 20};
+    const uint8_t trained = 1;
+    CKI(wr(f, &d, 4));
+    CKI(wr(f, &ntotal, 8));
+    CKI(wr(f, dummy, 16));
+    CKI(wr(f, &trained, 1));
+    return wr(f, &metric, 4);
+}
+
+extern "C" int b200_memo_write_headers(const char* path, const b200_memo_info* in, int64_t* rows_offset, int64_t* ids_offset) {
+    if (!path || !in || !rows_offset || !ids_offset) return fail("null argument");
+    if (in->d <= 0 || in->ntotal < 0 || in->kind < 0 || in->kind > 2 || (in->metric != B200_METRIC_IP && in->metric != B200_METRIC_L2))
+        return fail("bad index description");
+    FileGuard g;
+    g.f = fopen(path, "wb");
+    if (!g.f) return fail("could not open %s for writing: %s", path, strerror(errno));
+    if (in->kind) {
+        CKI(wr(g.f, in->kind == 2 ? "IxM2" : "IxMp", 4));
+        CKI(wr_header(g.f, in->d, in->ntotal, in->metric));
+    }
+    CKI(wr(g.f, in->metric == B200_METRIC_IP ? "IxFI" : "IxF2", 4));
+    CKI(wr_header(g.f, in->d, in->ntotal, in->metric));
+    const uint64_t count = (uint64_t)in->ntotal * (uint64_t)in->d;
+    CKI(wr(g.f, &count, 8));
+    *rows_offset = (int64_t)ftello(g.f);
+    *ids_offset = -1;
+    if (in->kind) {
+        const int64_t rows_end = *rows_offset + in->ntotal * (int64_t)in->d * 4;
+        if (fseeko(g.f, (off_t)rows_end, SEEK_SET) != 0) return fail("seek failed: %s", strerror(errno));
+        const uint64_t n_ids = (uint64_t)in->ntotal;
+        CKI(wr(g.f, &n_ids, 8));
+        *ids_offset = rows_end + 8;
+    }
+    if (fflush(g.f) != 0) return fail("write error: %s", strerror(errno));
+    return 0;
+}
+
+extern "C" int b200_index_save(b200_index* ix, const char* path, int kind) {
+    if (!ix || !path) return fail("null argument");
+    b200_memo_info info;
+    memset(&info, 0, sizeof info);
+    info.kind = kind;
+    info.d = ix->d;
+    info.metric = ix->metric;
+    info.ntotal = ix->ntotal;
+    int64_t rows_off = 0, ids_off = -1;
+    CKI(b200_memo_write_headers(path, &info, &rows_off, &ids_off));
+    return b200_index_write_file(ix, path, rows_off, ids_off);
+}
+
+extern "C" int b200_index_load(b200_index** out, const char* path, int store, int device, b200_memo_info* info_or_null) {
+    if (!out || !path) return fail("null argument");
+    *out = nullptr;
+    b200_memo_info info;
+    CKI(b200_memo_probe(path, &info));
+    if (info_or_null) *info_or_null = info;
+    b200_index* ix = nullptr;
+    CKI(b200_index_create(&ix, info.d, info.metric, store, device));
+    int rc = b200_index_add_file(ix, path, info.rows_offset, info.ntotal, info.ids_offset, 0);
+    if (rc) {
+        std::string keep = g_err;  // destroy must not lose the message
+        b200_index_destroy(ix);
+        g_err = keep;
+        return rc;
+    }
+    if (info.kind && info.ntotal == 0) ix->ids_state = 1;  // an empty id-mapped index stays id-mapped
+    *out = ix;
+    return 0;
+}
+
 extern "C" int b200_synth_rows_dev(float* out_dev, int64_t n, int d, uint64_t seed, int64_t first_row,
                                    int normalize, void* stream) {
     if (!out_dev || n < 0 || d <= 0) return fail("bad argument");

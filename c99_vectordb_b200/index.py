@@ -19,7 +19,6 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-import struct
 from types import SimpleNamespace
 
 import numpy as np
@@ -336,136 +335,37 @@ def normalize_L2(x: np.ndarray, device: int | None = None) -> None:
 # ------------------------------------------------------------------------------------------------
 # .memo files — faiss's native index serialisation [upstream layout]
 # ------------------------------------------------------------------------------------------------
-def _write_header(f, idx: Index, ntotal: int) -> None:
-    f.write(struct.pack("<i", idx.d))
-    f.write(struct.pack("<q", ntotal))
-    f.write(struct.pack("<q", 1 << 20))
-    f.write(struct.pack("<q", 1 << 20))
-    f.write(struct.pack("<B", 1))
-    f.write(struct.pack("<i", idx.metric_type))
-
-
-def _read_header(f):
-    d, = struct.unpack("<i", _read_exact(f, 4))
-    ntotal, _d1, _d2 = struct.unpack("<qqq", _read_exact(f, 24))
-    _trained, = struct.unpack("<B", _read_exact(f, 1))
-    metric, = struct.unpack("<i", _read_exact(f, 4))
-    if metric > 1:
-        _read_exact(f, 4)  # metric_arg
-    if d <= 0 or ntotal < 0:
-        raise RuntimeError("corrupt index header")
-    return d, ntotal, metric
-
-
-def _read_exact(f, n: int) -> bytes:
-    b = f.read(n)
-    if len(b) != n:
-        raise RuntimeError(f"read error: wanted {n} bytes, got {len(b)}")
-    return b
-
-
-def _write_flat_header(f, idx: IndexFlat) -> int:
-    """Flat index header up to and including the payload length; returns the payload's byte offset."""
-    f.write(b"IxFI" if idx.metric_type == METRIC_INNER_PRODUCT else b"IxF2")
-    n = idx.ntotal
-    _write_header(f, idx, n)
-    f.write(struct.pack("<Q", n * idx.d))  # code bytes / 4
-    return f.tell()
-
-
 def write_index(index: Index, path: str) -> None:
     """faiss.write_index (memo_cli.py:361, :448).  bf16-stored rows are widened to fp32 (lossless).
-    Headers are written here; the rows and ids go device -> pinned ring -> file inside
-    b200_index_write_file (no intermediate numpy copies)."""
+    The library writes the faiss headers (b200_memo_write_headers) and moves the rows and ids
+    device -> pinned ring -> file (b200_index_write_file); nothing passes through numpy."""
     path = os.fspath(path)
     if isinstance(index, IndexIDMap):
-        base, with_ids = index.index, True
+        base, kind = index.index, (2 if isinstance(index, IndexIDMap2) else 1)
     elif isinstance(index, IndexFlat):
-        base, with_ids = index, False
+        base, kind = index, 0
     else:
         raise RuntimeError(f"don't know how to serialize {type(index).__name__}")
-    n = base.ntotal
-    with open(path, "wb") as f:
-        if with_ids:
-            f.write(index._fourcc)
-            _write_header(f, index, n)
-        rows_off = _write_flat_header(f, base)
-        ids_off = -1
-        if with_ids:
-            f.seek(rows_off + n * base.d * 4)
-            f.write(struct.pack("<Q", n))
-            ids_off = f.tell()
-    if n:
-        _cabi.check(_cabi.load().b200_index_write_file(base._h, path.encode(), rows_off, ids_off))
-
-
-def _read_any(f, path: str, device):
-    fourcc = _read_exact(f, 4)
-    if fourcc in (b"IxMp", b"IxM2"):
-        d, ntotal, metric = _read_header(f)
-        # the nested flat payload must be added together with the ids that follow it
-        base, rows_off, n = _read_flat_payload(f, device)
-        f.seek(rows_off + n * base.d * 4)
-        n_ids, = struct.unpack("<Q", _read_exact(f, 8))
-        if n_ids != n:
-            raise RuntimeError("id_map size does not match the nested index")
-        ids_off = f.tell()
-        wrapper = (IndexIDMap2 if fourcc == b"IxM2" else IndexIDMap)(base)
-        if n:
-            _cabi.check(_cabi.load().b200_index_add_file(base._h, path.encode(), rows_off, n, ids_off, 0))
-        return wrapper
-    f.seek(-4, os.SEEK_CUR)
-    base, rows_off, n = _read_flat_payload(f, device)
-    if n:
-        _cabi.check(_cabi.load().b200_index_add_file(base._h, path.encode(), rows_off, n, -1, 0))
-    return base
-
-
-def _skip_vector(f, elem_bytes: int, limit: int) -> int:
-    n, = struct.unpack("<Q", _read_exact(f, 8))
-    if n > limit:
-        raise RuntimeError("implausible vector length in index file")
-    f.seek(n * elem_bytes, os.SEEK_CUR)
-    return n
-
-
-def _skip_hnsw_graph(f, ntotal: int) -> None:
-    """memo's original files are IndexIDMap2 -> IndexHNSWFlat ("IHNf", memo_cli.py:244-248): header,
-    the HNSW graph, then the flat storage index.  The graph is useless for an exact flat index, so
-    it is skipped: assign_probas (double), cum_nneighbor_per_level (int32), levels (int32, one per
-    vector), offsets (size_t, ntotal+1), neighbors (int32), then entry_point, max_level,
-    efConstruction, efSearch, upper_beam (5 x int32) [upstream write_HNSW layout, unverified here —
-    every size is checked and a mismatch raises, which memo treats as an unreadable file]."""
-    big = 1 << 40
-    _skip_vector(f, 8, 1 << 16)
-    _skip_vector(f, 4, 1 << 16)
-    if _skip_vector(f, 4, big) != ntotal:
-        raise RuntimeError("HNSW levels do not match ntotal")
-    if _skip_vector(f, 8, big) != ntotal + 1:
-        raise RuntimeError("HNSW offsets do not match ntotal")
-    _skip_vector(f, 4, big)
-    _read_exact(f, 20)
-
-
-def _read_flat_payload(f, device):
-    fourcc = _read_exact(f, 4)
-    if fourcc == b"IHNf":
-        _d, ntotal, _metric = _read_header(f)
-        _skip_hnsw_graph(f, ntotal)
-        fourcc = _read_exact(f, 4)  # the storage index
-    if fourcc not in (b"IxFI", b"IxF2", b"IxFl"):
-        raise RuntimeError(f"Index type {fourcc!r} not recognized")
-    d, ntotal, metric = _read_header(f)
-    count, = struct.unpack("<Q", _read_exact(f, 8))
-    if count != ntotal * d:
-        raise RuntimeError("flat payload size does not match header")
-    base = IndexFlat(d, metric, device=device)
-    return base, f.tell(), ntotal
+    L = _cabi.load()
+    info = _cabi.MemoInfo(kind=kind, d=base.d, metric=base.metric_type, ntotal=base.ntotal)
+    rows_off, ids_off = C.c_int64(0), C.c_int64(-1)
+    _cabi.check(L.b200_memo_write_headers(path.encode(), C.byref(info), C.byref(rows_off), C.byref(ids_off)))
+    if info.ntotal:
+        _cabi.check(L.b200_index_write_file(base._h, path.encode(), rows_off.value, ids_off.value))
 
 
 def read_index(path: str, device: int | None = None) -> Index:
     """faiss.read_index (memo_cli.py:255): raises on a missing or corrupt file (memo catches
-    Exception and starts a fresh index, :256-257)."""
+    Exception and starts a fresh index, :256-257).  The library parses the headers (b200_memo_probe:
+    IxM2 / IxMp wrappers, flat payloads, memo's own IHNf files with the graph skipped) and streams the
+    payload file -> pinned ring -> device (b200_index_add_file)."""
     path = os.fspath(path)
-    with open(path, "rb") as f:
-        return _read_any(f, path, device)
+    os.stat(path)  # FileNotFoundError for a missing file, like open()
+    L = _cabi.load()
+    info = _cabi.MemoInfo()
+    _cabi.check(L.b200_memo_probe(path.encode(), C.byref(info)))
+    base = IndexFlat(info.d, info.metric, device=device)
+    out = base if info.kind == 0 else (IndexIDMap2 if info.kind == 2 else IndexIDMap)(base)
+    if info.ntotal:
+        _cabi.check(L.b200_index_add_file(base._h, path.encode(), info.rows_offset, info.ntotal, info.ids_offset, 0))
+    return out

@@ -102,6 +102,33 @@ int b200_index_add_dev(b200_index* ix, const float* x_dev, int64_t n, const int6
 int b200_index_add_file(b200_index* ix, const char* path, int64_t rows_offset, int64_t n,
                         int64_t ids_offset, int normalize);
 int b200_index_write_file(b200_index* ix, const char* path, int64_t rows_offset, int64_t ids_offset);
+
+/* ---- whole .memo files (faiss index serialisation) -------------------------
+ * replaces: faiss.read_index(str) memo_cli.py:255 / faiss.write_index(index, str) memo_cli.py:361, :448
+ *           (faiss's own C API: faiss_read_index_fname / faiss_write_index_fname [upstream]).
+ * Layouts understood: IndexIDMap ("IxMp") / IndexIDMap2 ("IxM2") over a flat index ("IxFI" / "IxF2" /
+ * "IxFl"), a bare flat index, and memo's original files whose nested index is IndexHNSWFlat ("IHNf"):
+ * the graph is skipped and the flat storage behind it is used (every size is checked).  Written files
+ * are plain flat indexes ("IxFI" for IP, "IxF2" for L2) with or without the id-map wrapper.
+ *   b200_memo_probe          parse the headers only (no device needed): what is in the file and where
+ *   b200_memo_write_headers  create/truncate `path`, write every header (and the id count), report the
+ *                            payload offsets that b200_index_write_file then fills
+ *   b200_index_save          headers + payload of a resident index; kind 0 = bare flat, 1 = IxMp, 2 = IxM2
+ *                            (an index added without ids saves its row positions as ids)
+ *   b200_index_load          probe + create + add_file: a new handle holding the file's rows (and ids) */
+typedef struct b200_memo_info {
+    int32_t kind;        /* 0 = flat index, 1 = IndexIDMap, 2 = IndexIDMap2 */
+    int32_t d;
+    int32_t metric;      /* B200_METRIC_* of the flat payload */
+    int32_t from_hnsw;   /* 1: the payload sat behind an IndexHNSWFlat graph that was skipped */
+    int64_t ntotal;
+    int64_t rows_offset; /* byte offset of ntotal * d float32 */
+    int64_t ids_offset;  /* byte offset of ntotal int64, or -1 */
+} b200_memo_info;
+int b200_memo_probe(const char* path, b200_memo_info* out);
+int b200_memo_write_headers(const char* path, const b200_memo_info* in, int64_t* rows_offset, int64_t* ids_offset);
+int b200_index_save(b200_index* ix, const char* path, int kind);
+int b200_index_load(b200_index** out, const char* path, int store, int device, b200_memo_info* info_or_null);
 /* synthetic rows generated on the device by the counter-based generator of DESIGN.md §6
  * (bit-identical to oracle/flat_oracle.c:oracle_synth_rows); rows get ids first_id + i when
  * with_ids != 0.  Used by bench.py / tests for databases too large to upload. */

@@ -45,7 +45,10 @@ class FakeLib:
         return 1
 
     def b200_last_error(self):
-        return self._err
+        if self._err:  # the last failure came from a faked entry point
+            e, self._err = self._err, b""
+            return e
+        return self._real.b200_last_error()
 
     def _ix(self, h) -> _Idx:
         return self._tab[h.value if hasattr(h, "value") else int(h)]

@@ -52,17 +52,41 @@ def test_product_never_imports_oracle():
         assert "flat_oracle" not in src or p.suffix in (".cu", ".cuh"), p  # kernels only cite it in comments
 
 
-def test_faiss_header_layout_roundtrip():
-    fake = SimpleNamespace(d=384, metric_type=1)
-    buf = io.BytesIO()
-    ix._write_header(buf, fake, 12345)
-    raw = buf.getvalue()
-    assert len(raw) == 4 + 8 + 8 + 8 + 1 + 4
-    assert struct.unpack("<i", raw[:4])[0] == 384 and struct.unpack("<q", raw[4:12])[0] == 12345
-    buf.seek(0)
-    assert ix._read_header(buf) == (384, 12345, 1)
-    with pytest.raises(RuntimeError):
-        ix._read_header(io.BytesIO(raw[:10]))
+def test_faiss_header_layout_roundtrip(tmp_path):
+    """b200_memo_write_headers / b200_memo_probe are host code: the faiss layout is
+    written and parsed by the real library without a device."""
+    import ctypes as C
+
+    from c99_vectordb_b200 import _cabi
+
+    L = _cabi.load()
+    p = tmp_path / "h.memo"
+    d, n = 384, 3
+    info = _cabi.MemoInfo(kind=2, d=d, metric=1, ntotal=n)
+    ro, io_ = C.c_int64(), C.c_int64()
+    assert L.b200_memo_write_headers(str(p).encode(), C.byref(info), C.byref(ro), C.byref(io_)) == 0
+    hdr = struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, 1)
+    assert len(hdr) == 4 + 8 + 8 + 8 + 1 + 4
+    raw = p.read_bytes()
+    assert raw[:4] == b"IxM2" and raw[4:37] == hdr and raw[37:41] == b"IxF2" and raw[41:74] == hdr
+    assert struct.unpack("<Q", raw[74:82])[0] == n * d and ro.value == 82
+    assert io_.value == 82 + n * d * 4 + 8 and struct.unpack("<Q", raw[io_.value - 8:io_.value])[0] == n
+    got = _cabi.MemoInfo()
+    assert L.b200_memo_probe(str(p).encode(), C.byref(got)) != 0  # the payload is not there yet
+    assert b"shorter" in L.b200_last_error()
+    with open(p, "r+b") as f:
+        f.seek(io_.value)
+        f.write(b"\0" * (n * 8))
+    assert L.b200_memo_probe(str(p).encode(), C.byref(got)) == 0
+    assert (got.kind, got.d, got.metric, got.ntotal, got.rows_offset, got.ids_offset, got.from_hnsw) == (2, d, 1, n, 82, io_.value, 0)
+    info = _cabi.MemoInfo(kind=0, d=8, metric=0, ntotal=0)
+    assert L.b200_memo_write_headers(str(p).encode(), C.byref(info), C.byref(ro), C.byref(io_)) == 0
+    assert p.read_bytes() == b"IxFI" + struct.pack("<iqqqBi", 8, 0, 1 << 20, 1 << 20, 1, 0) + struct.pack("<Q", 0) and io_.value == -1
+    assert L.b200_memo_probe(str(p).encode(), C.byref(got)) == 0 and (got.kind, got.ntotal, got.ids_offset) == (0, 0, -1)
+    assert L.b200_memo_probe(str(tmp_path / "missing").encode(), C.byref(got)) != 0
+    assert b"could not open" in L.b200_last_error()
+    bad = _cabi.MemoInfo(kind=3, d=8, metric=0, ntotal=0)
+    assert L.b200_memo_write_headers(str(p).encode(), C.byref(bad), C.byref(ro), C.byref(io_)) != 0
 
 
 def test_read_index_rejects_garbage(tmp_path):

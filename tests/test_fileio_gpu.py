@@ -109,5 +109,46 @@ def test_truncated_payload_raises(b200, tmp_path, cut):
 def test_write_to_unwritable_path_raises(b200, tmp_path):
     idx = b200.IndexFlatL2(8)
     idx.add(np.ones((3, 8), np.float32))
-    with pytest.raises(OSError):
+    with pytest.raises((OSError, RuntimeError), match="No such file"):
         b200.write_index(idx, str(tmp_path / "no_such_dir" / "x.memo"))
+
+
+def test_c_level_save_and_load(b200, tmp_path):
+    """b200_index_save / b200_index_load: what a cgo / JNI host binds instead of faiss_write_index_fname /
+    faiss_read_index_fname [upstream C API] — whole files, no Python header code involved."""
+    import ctypes as C
+
+    from c99_vectordb_b200 import _cabi
+
+    L = _cabi.load()
+    d, n = 48, 3000
+    db = oracle.synth_rows(n, d, 41)
+    ids = np.arange(n, dtype=np.int64) * 11 + 5
+    idx = b200.IndexIDMap2(b200.IndexFlat(d, 0))
+    idx.add_with_ids(db, ids)
+    p = str(tmp_path / "c.memo").encode()
+    _cabi.check(L.b200_index_save(idx.index._h, p, 2))
+    assert open(p, "rb").read() == _expected_file(d, 0, db, ids)
+    h, info = C.c_void_p(), _cabi.MemoInfo()
+    _cabi.check(L.b200_index_load(C.byref(h), p, 0, 0, C.byref(info)))
+    try:
+        assert (info.kind, info.d, info.metric, info.ntotal) == (2, d, 0, n)
+        assert L.b200_index_ntotal(h) == n and L.b200_index_has_ids(h) == 1
+        q = oracle.synth_rows(2, d, 42)
+        D = np.empty((2, 7), np.float32)
+        I = np.empty((2, 7), np.int64)
+        _cabi.check(L.b200_index_search(h, q.ctypes.data, 2, 7, D.ctypes.data, I.ctypes.data))
+        Dw, Iw = idx.search(q, 7)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)
+    finally:
+        L.b200_index_destroy(h)
+    # a bare flat index, bf16-resident after load
+    _cabi.check(L.b200_index_save(idx.index._h, p, 0))
+    _cabi.check(L.b200_index_load(C.byref(h), p, 1, 0, None))
+    try:
+        assert L.b200_index_ntotal(h) == n and L.b200_index_has_ids(h) == 0 and L.b200_index_store(h) == 1
+    finally:
+        L.b200_index_destroy(h)
+    open(p, "wb").write(b"IxF2 nonsense")
+    assert L.b200_index_load(C.byref(h), p, 0, 0, None) != 0 and not h.value
