@@ -111,3 +111,11 @@ def device_count() -> int:
     n = C.c_int(0)
     check(load().b200_device_count(C.byref(n)))
     return n.value
+
+
+def device_count_or_zero() -> int:
+    """Number of CUDA devices, 0 when the driver is absent (used by tests to tell a GPU box from a build box)."""
+    try:
+        return device_count()
+    except RuntimeError:
+        return 0

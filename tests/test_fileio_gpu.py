@@ -152,3 +152,26 @@ def test_c_level_save_and_load(b200, tmp_path):
         L.b200_index_destroy(h)
     open(p, "wb").write(b"IxF2 nonsense")
     assert L.b200_index_load(C.byref(h), p, 0, 0, None) != 0 and not h.value
+
+
+def test_c99_example_program(b200, tmp_path):
+    """examples/memo_recall.c, compiled with gcc -std=c99 -Wpedantic -Werror, loads a .memo file and searches."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from test_c_example_cpu import build_example, write_memo
+
+    exe = build_example(tmp_path)
+    d, n = 384, 500
+    db = oracle.normalize_rows(oracle.synth_rows(n, d, 51))
+    ids = np.arange(n, dtype=np.int64) + 1000
+    write_memo(tmp_path / "e.memo", db, ids)
+    r = subprocess.run([str(exe), str(tmp_path / "e.memo"), "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert "id-mapped index, d=384, L2, 500 rows" in lines[0]
+    assert lines[1].split()[:3] == ["1", "id", "1000"] and float(lines[1].split()[-1]) == 0.0
+    Dw, Iw = oracle.search(1, db, db[:1], 3, ids=ids, order=oracle.ORDER_DEVICE)
+    assert [int(l.split()[2]) for l in lines[1:4]] == Iw[0].tolist()
