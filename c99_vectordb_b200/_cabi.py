@@ -57,6 +57,8 @@ SIGNATURES = [
     ("b200_exchange_slot_bytes", C.c_size_t, []),
     ("b200_index_set_exchange", C.c_int, [_h, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     ("b200_index_search_exchange_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("b200_index_exchange_status", C.c_int, [_h]),
+    ("b200_index_read_phase_stamps", C.c_int, [_h, C.c_void_p, C.c_int64, _ip]),
     ("b200_index_launch_count", C.c_int64, [_h]),
     ("b200_index_sync", C.c_int, [_h]),
     ("b200_index_ntotal", C.c_int64, [_h]),

@@ -52,17 +52,29 @@ def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared",)]
     nvcc = nvcc_path()
 
-    def compile_one(cu: Path) -> Path:
-        obj = objdir / (cu.stem + ".o")
-        cmd = [nvcc, *compile_flags, "-c"]
+    # the scan kernel templates are compiled once per (metric, store) pair so that the build parallelises
+    jobs: list[tuple[Path, list[str], str]] = []
+    for cu in cus:
+        if cu.stem in ("scan_bulk", "scan_ldg"):
+            for m in (0, 1):
+                for st in (0, 1):
+                    jobs.append((cu, [f"-DSCAN_M={m}", f"-DSCAN_S={st}"], f"{cu.stem}_m{m}_s{st}"))
+        else:
+            jobs.append((cu, [], cu.stem))
+
+    def compile_one(job) -> Path:
+        cu, defines, name = job
+        obj = objdir / (name + ".o")
+        cmd = [nvcc, *compile_flags, *defines, "-c"]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         cmd += ["-o", str(obj), str(cu)]
         subprocess.run(cmd, check=True)
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(cus)) as pool:
-        objs = list(pool.map(compile_one, cus))
+    jobs.sort(key=lambda j: 0 if j[0].stem.startswith("scan_") or j[0].stem == "cabi" else 1)  # long jobs first
+    with ThreadPoolExecutor(max_workers=max(1, os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(compile_one, jobs))
     subprocess.run([nvcc, *NVCC_FLAGS, "-o", str(LIB)] + [str(o) for o in objs], check=True)
     return LIB
 

@@ -24,8 +24,10 @@
 #include "rows.cuh"
 #include "scan_topk.cuh"
 
-// one (parity, sender) slot of the fused exchange: 16-byte header (epoch flag) + 8 queries x 256 results
-#define XCHG_SLOT_BYTES ((size_t)16 + (size_t)8 * B200_FUSED_K_MAX * 12)
+// one (parity, sender) slot of the fused exchange: 16 spare bytes + up to 4096 entries of three self-validating
+// 8-byte words (id low | epoch, id high | epoch, score bits | epoch)
+#define XCHG_MAX_ENTRIES 4096
+#define XCHG_SLOT_BYTES ((size_t)16 + (size_t)XCHG_MAX_ENTRIES * 24)
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -69,9 +71,19 @@ struct b200_index {
     int num_sms = 0;
     size_t smem_optin = 0;
     // scratch
-    uint64_t* partials = nullptr;
-    size_t partials_cap = 0;  // keys
-    unsigned int* ticket = nullptr;
+    // per-launch control words and survivor lists of the scan kernel, double-buffered by launch parity so that
+    // back-to-back launches may overlap (programmatic dependent launch)
+    uint64_t* partials = nullptr;   // [2][grid, QB, warps*k]
+    size_t partials_cap = 0;        // keys per parity set
+    unsigned int* part_count = nullptr;  // [2][grid, QB]
+    size_t part_count_cap = 0;           // words per parity set
+    unsigned long long* ctl = nullptr;   // [2][16]: word 0 = {ticket, tile counter}, words 1..8 = thresholds per query
+    uint64_t launch_seq = 0;
+    unsigned long long* stamps = nullptr;  // [grid, 8] phase stamps of the last scan launch (option scan_phase_stamps)
+    size_t stamps_cap = 0;
+    int stamps_grid = 0;
+    cudaStream_t last_stream = nullptr;  // the stream the handle's scratch was last used on
+    cudaEvent_t order_ev = nullptr;
     float* q_dev = nullptr;   // staged host queries
     float* qn_dev = nullptr;  // normalised queries
     size_t q_cap = 0, qn_cap = 0;  // floats
@@ -89,7 +101,9 @@ struct b200_index {
     // options
     int64_t opt_variant = B200_SCAN_AUTO, opt_warps = 16, opt_stages = 0, opt_tile_rows = 0,
             opt_ctas_per_sm = 0, opt_evict_first = 0, opt_fullrank_min_k = B200_FUSED_K_MAX + 1,
-            opt_normalize_queries = 0, opt_staged_results = 1, opt_qb = 0, opt_dynamic = -1, opt_claim_chunk = 0, opt_fused_tail = -1;
+            opt_normalize_queries = 0, opt_staged_results = 1, opt_qb = 0, opt_dynamic = -1, opt_claim_chunk = 0, opt_fused_tail = -1,
+            opt_claim_min = 0, opt_pdl = 1, opt_queries_stable = 0, opt_phase_stamps = 0, opt_fuse_query_norm = 1;
+    bool cur_norm_q = false;  // the scan launches of the search in flight normalise their queries themselves
     int64_t opt_gemm_min_rows = 4096, opt_gemm_min_nq = 2, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2;
     // read-only statistics of the last batched (K3) search
     int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
@@ -135,6 +149,19 @@ struct b200_index {
 
 static int use_device(b200_index* ix) {
     CK(cudaSetDevice(ix->device));
+    return 0;
+}
+
+// All device work of a handle shares its scratch (control words, survivor lists, staged queries ...), so work enqueued
+// on a different stream than the previous call's must be ordered behind it: an event recorded at the tail of the stream
+// used last (which still exists: streams handed to this library must outlive the handle's use of them) and waited for
+// on the new one.  Nothing is recorded while the caller stays on one stream.
+static int order_after_previous_stream(b200_index* ix, cudaStream_t st) {
+    if (ix->last_stream != st && ix->last_stream != nullptr) {
+        CK(cudaEventRecord(ix->order_ev, ix->last_stream));
+        CK(cudaStreamWaitEvent(st, ix->order_ev, 0));
+    }
+    ix->last_stream = st;
     return 0;
 }
 
@@ -213,8 +240,9 @@ extern "C" int b200_index_create(b200_index** out, int d, int metric, int store,
     ix->num_sms = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ix->ticket, 2 * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(ix->ticket, 0, 2 * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ix->ctl, 2 * 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(ix->ctl, 0, 2 * 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->order_ev, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete ix;
         return fail("index create: %s", cudaGetErrorString(e));
@@ -230,7 +258,10 @@ extern "C" int b200_index_destroy(b200_index* ix) {
     cudaFree(ix->rows);
     cudaFree(ix->ids);
     cudaFree(ix->partials);
-    cudaFree(ix->ticket);
+    cudaFree(ix->part_count);
+    cudaFree(ix->ctl);
+    cudaFree(ix->stamps);
+    if (ix->order_ev) cudaEventDestroy(ix->order_ev);
     cudaFree(ix->q_dev);
     cudaFree(ix->qn_dev);
     cudaFree(ix->D_dev);
@@ -270,6 +301,7 @@ extern "C" int b200_index_destroy(b200_index* ix) {
 extern "C" int b200_index_reset(b200_index* ix) {
     if (!ix) return fail("null index");
     CKI(use_device(ix));
+    CKI(order_after_previous_stream(ix, ix->stream));
     CK(cudaStreamSynchronize(ix->stream));
     ix->ntotal = 0;
     ix->ids_state = 0;
@@ -334,6 +366,11 @@ static const OptName kOpts[] = {
     {"scan_dynamic_tiles", &b200_index::opt_dynamic},
     {"scan_claim_chunk", &b200_index::opt_claim_chunk},
     {"scan_fused_tail", &b200_index::opt_fused_tail},
+    {"scan_claim_min", &b200_index::opt_claim_min},
+    {"scan_pdl", &b200_index::opt_pdl},
+    {"queries_stable", &b200_index::opt_queries_stable},
+    {"scan_phase_stamps", &b200_index::opt_phase_stamps},
+    {"fuse_query_normalize", &b200_index::opt_fuse_query_norm},
     {"gemm_min_nq", &b200_index::opt_gemm_min_nq},
     {"gemm_min_rows", &b200_index::opt_gemm_min_rows},
     {"gemm_emit_factor", &b200_index::opt_gemm_emit_factor},
@@ -581,6 +618,7 @@ static int add_common(b200_index* ix, const float* x, bool x_is_dev, int64_t n, 
     if (!x && !file) return fail("x is null");
     const bool with_ids = ids != nullptr || (file && ids_file_off >= 0);
     CKI(use_device(ix));
+    CKI(order_after_previous_stream(ix, ix->stream));
     CKI(note_ids(ix, with_ids));
     CKI(ensure_capacity(ix, ix->ntotal + n, with_ids));
     cudaStream_t st = ix->stream;
@@ -938,6 +976,7 @@ extern "C" int b200_index_add_synthetic(b200_index* ix, int64_t n, uint64_t seed
     if (n < 0) return fail("negative n");
     if (n == 0) return 0;
     CKI(use_device(ix));
+    CKI(order_after_previous_stream(ix, ix->stream));
     CKI(note_ids(ix, with_ids != 0));
     CKI(ensure_capacity(ix, ix->ntotal + n, with_ids != 0));
     cudaStream_t st = ix->stream;
@@ -987,11 +1026,29 @@ typedef void (*ScanFn)(const ScanParams);
 // The scan kernel instantiations live in scan_bulk.cu / scan_ldg.cu (separate translation units so
 // the build parallelises): 32 lanes per row with query blocks 1/2/4/8, 16 lanes per row (short rows)
 // with query blocks 1 and 8.
-ScanFn b200_pick_scan_bulk(int metric, int store, int qb, int lpr);
-ScanFn b200_pick_scan_ldg(int metric, int store, int qb, int lpr);
+#define SCAN_DECL(V) \
+    ScanFn b200_pick_scan_##V##_m0_s0(int, int); ScanFn b200_pick_scan_##V##_m0_s1(int, int); \
+    ScanFn b200_pick_scan_##V##_m1_s0(int, int); ScanFn b200_pick_scan_##V##_m1_s1(int, int);
+SCAN_DECL(bulk) SCAN_DECL(ldg)
+#undef SCAN_DECL
 static ScanFn pick_scan(int metric, int store, int qb, int variant, int lpr) {
-    return variant == B200_VARIANT_BULK ? b200_pick_scan_bulk(metric, store, qb, lpr)
-                                        : b200_pick_scan_ldg(metric, store, qb, lpr);
+    const int ms = metric * 2 + store;
+    if (variant == B200_VARIANT_BULK) {
+        switch (ms) {
+            case 0: return b200_pick_scan_bulk_m0_s0(qb, lpr);
+            case 1: return b200_pick_scan_bulk_m0_s1(qb, lpr);
+            case 2: return b200_pick_scan_bulk_m1_s0(qb, lpr);
+            case 3: return b200_pick_scan_bulk_m1_s1(qb, lpr);
+        }
+    } else {
+        switch (ms) {
+            case 0: return b200_pick_scan_ldg_m0_s0(qb, lpr);
+            case 1: return b200_pick_scan_ldg_m0_s1(qb, lpr);
+            case 2: return b200_pick_scan_ldg_m1_s0(qb, lpr);
+            case 3: return b200_pick_scan_ldg_m1_s1(qb, lpr);
+        }
+    }
+    return nullptr;
 }
 
 typedef void (*MergeFn)(const ScanParams, uint32_t);
@@ -1044,10 +1101,10 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
                 uint32_t tr = m * step_rows;
                 uint64_t tile_bytes = (uint64_t)tr * ix->pitch;
                 if (tile_bytes > (1u << 19)) continue;  // mbarrier tx-count headroom
-                uint32_t scratch = std::max<uint32_t>(B200_FINAL_BUF_KEYS, next_pow2((uint32_t)(nw * kk)));
+                const uint32_t scratch = B200_FINAL_BUF_KEYS;
                 size_t fixed = scan_smem_bytes(B200_VARIANT_BULK, nw, qb, qstride, kk, fullrank, 0, 0, scratch);
                 // ring replaces the scratch region when larger
-                size_t fixed_wo_scratch = fixed - (((size_t)scratch * 8 + 127) & ~(size_t)127);
+                size_t fixed_wo_scratch = fixed - (((size_t)scratch * 8 + B200_PREF_BYTES + 127) & ~(size_t)127);
                 if (fixed_wo_scratch + 64 >= budget) continue;
                 size_t avail = budget - fixed_wo_scratch - 64;
                 uint32_t stages = (uint32_t)std::min<uint64_t>(8, avail / ((uint64_t)nw * tile_bytes + (uint64_t)nw * 12));
@@ -1072,7 +1129,7 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
         int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_LDG / 32);
         for (;; nw >>= 1) {
             if (nw < 1) return fail("k=%d does not fit the fused top-k shared-memory budget", k);
-            uint32_t scratch = std::max<uint32_t>(B200_FINAL_BUF_KEYS, next_pow2((uint32_t)(nw * kk)));
+            const uint32_t scratch = B200_FINAL_BUF_KEYS;
             size_t smem = scan_smem_bytes(B200_VARIANT_LDG, nw, qb, qstride, kk, fullrank, 0, 0, scratch);
             if (smem > budget) continue;
             pl.variant = B200_VARIANT_LDG;
@@ -1118,16 +1175,22 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     p.qstride = (ix->d_pad + 7) / 8 * 8;
     p.nqb = nqb;
     p.k = score_keys ? 1 : k;
-    p.ticket = ix->ticket;
+    p.normalize_q = ix->cur_norm_q ? 1 : 0;
+    const int set = (int)(ix->launch_seq++ & 1);  // control words and survivor lists of this launch's parity
+    p.ticket = reinterpret_cast<unsigned int*>(ix->ctl + (size_t)set * 16);
+    p.gtau = ix->ctl + (size_t)set * 16 + 1;
     p.dynamic = ix->opt_dynamic < 0 ? (pl.variant == B200_VARIANT_BULK ? 1 : 0) : (ix->opt_dynamic ? 1 : 0);
     {
         // One atomic claim hands out a run of tiles.  The run bounds the tail (a warp finishes at
         // most one run after the database is exhausted: run x ~2 us) while a single hot counter
-        // sustains only ~400 claims/us; >= 64 claims per warp, runs of 4..16 tiles.
+        // sustains only ~400 claims/us; >= 64 claims per warp, runs of 4..16 tiles that shrink to
+        // claim_min towards the end (guided self-scheduling in the kernel).
         uint64_t tiles = ((uint64_t)ix->ntotal + pl.tile_rows - 1) / pl.tile_rows;
         uint64_t per = tiles / ((uint64_t)pl.grid * pl.nw * 64);
         p.claim_chunk = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(per, 4), 16);
         if (ix->opt_claim_chunk > 0) p.claim_chunk = (uint32_t)ix->opt_claim_chunk;
+        p.claim_min = ix->opt_claim_min > 0 ? (uint32_t)ix->opt_claim_min : 2u;
+        if (p.claim_min > p.claim_chunk) p.claim_min = p.claim_chunk;
     }
     p.fused_tail = (nqb == 1 || score_keys) ? 1 : 0;
     if (ix->opt_fused_tail >= 0) p.fused_tail = ix->opt_fused_tail ? 1 : 0;
@@ -1143,6 +1206,8 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     p.row_mask = ix->cur_mask;
     p.scratch_keys = pl.scratch_keys;
     if (ix->xchg_active && !score_keys) {
+        if ((int64_t)ix->xchg_world * nqb * k > XCHG_MAX_ENTRIES)
+            return fail("fused exchange: world x queries x k = %lld entries exceed %d", (long long)ix->xchg_world * nqb * k, XCHG_MAX_ENTRIES);
         p.xchg_peers = ix->xchg_peers_dev;
         p.xchg_world = ix->xchg_world;
         p.xchg_rank = ix->xchg_rank;
@@ -1151,20 +1216,64 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
         p.xchg_status = ix->xchg_status;
         p.fused_tail = 1;  // the exchange lives in the last CTA's tail
     }
+    if (pl.grid > 1023) return fail("scan grid of %d CTAs exceeds the final merge's prefix table", pl.grid);
     if (!score_keys) {
-        size_t need = (size_t)pl.grid * pl.qb * k;
-        CKI(grow(&ix->partials, &ix->partials_cap, need));
+        p.part_cap = (uint32_t)(pl.nw * k);
+        const size_t need = (size_t)pl.grid * pl.qb * p.part_cap, need_c = (size_t)pl.grid * pl.qb;
+        if (ix->partials_cap < need || ix->part_count_cap < need_c) {
+            CK(cudaStreamSynchronize(st));  // launches in flight still use the old buffers
+            if (ix->partials_cap < need) {
+                if (ix->partials) CK(cudaFree(ix->partials));
+                ix->partials = nullptr;
+                ix->partials_cap = 0;
+                CK(cudaMalloc((void**)&ix->partials, 2 * need * sizeof(uint64_t)));
+                ix->partials_cap = need;
+            }
+            if (ix->part_count_cap < need_c) {
+                if (ix->part_count) CK(cudaFree(ix->part_count));
+                ix->part_count = nullptr;
+                ix->part_count_cap = 0;
+                CK(cudaMalloc((void**)&ix->part_count, 2 * need_c * sizeof(unsigned int)));
+                ix->part_count_cap = need_c;
+            }
+        }
+        p.partials = ix->partials + (size_t)set * ix->partials_cap;
+        p.part_count = ix->part_count + (size_t)set * ix->part_count_cap;
     }
-    p.partials = ix->partials;
+    if (ix->opt_phase_stamps) {
+        const size_t need = (size_t)pl.grid * 8;
+        if (ix->stamps_cap < need) {
+            CK(cudaStreamSynchronize(st));
+            CKI(grow(&ix->stamps, &ix->stamps_cap, need));
+        }
+        CK(cudaMemsetAsync(ix->stamps, 0, need * sizeof(unsigned long long), st));
+        p.stamps = ix->stamps;
+        ix->stamps_grid = pl.grid;
+    }
     ScanFn fn = pick_scan(ix->metric, ix->store, pl.qb, pl.variant, ix->lpr);
     if (!fn) return fail("no scan kernel for metric=%d store=%d qb=%d variant=%d", ix->metric, ix->store, pl.qb, pl.variant);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    fn<<<pl.grid, pl.nw * 32, pl.smem, st>>>(p);
+    // Programmatic dependent launch: a search that follows another kernel on this stream may start while that kernel
+    // drains (its CTAs take SMs as they free up).  pdl = 1: the kernel waits for its predecessor before it reads the
+    // queries; pdl = 2 (option queries_stable: the caller promises that the queries are not produced by the preceding
+    // kernel on the stream): it waits only after its scan, before it publishes anything.
+    p.pdl = ix->opt_pdl ? (ix->opt_queries_stable ? 2 : 1) : 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)pl.grid);
+    cfg.blockDim = dim3((unsigned)(pl.nw * 32));
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, fn, p));
     ++ix->launches;
-    CK(cudaGetLastError());
     if (!score_keys && !p.fused_tail) {
         MergeFn mf = pick_merge(ix->metric, pl.qb);
-        size_t msmem = (size_t)pl.scratch_keys * 8 + 16;
+        size_t msmem = (size_t)pl.scratch_keys * 8 + 16 + B200_PREF_BYTES;
         mf<<<nqb, 256, msmem, st>>>(p, (uint32_t)pl.grid);
         ++ix->launches;
         CK(cudaGetLastError());
@@ -1576,6 +1685,7 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
     if (nq * k > ((int64_t)1 << 40)) return fail("result too large");
     CKI(use_device(ix));
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    CKI(order_after_previous_stream(ix, st));
     if (ix->ntotal == 0) {
         int64_t count = nq * k;
         unsigned blocks = (unsigned)((count + 255) / 256);
@@ -1587,19 +1697,28 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
         CK(cudaGetLastError());
         return 0;
     }
-    if (ix->opt_normalize_queries) {
-        if (ix->qn_cap < (size_t)nq * ix->d) {
-            CK(cudaStreamSynchronize(st));
-            CKI(grow(&ix->qn_dev, &ix->qn_cap, (size_t)nq * ix->d));
-        }
-        CKI(ingest_dev(ix->d, ix->d, B200_STORE_F32, q_dev, (uint8_t*)ix->qn_dev, (size_t)ix->d * 4, nq, 1,
-                       ix->num_sms, st, &ix->launches));
-        q_dev = ix->qn_dev;
-    }
     const bool fullrank = k >= ix->opt_fullrank_min_k || k > B200_FUSED_K_MAX;
+    const bool use_gemm = !fullrank && !ix->xchg_active && gemm_eligible(ix, nq, k) && ix->sh_failed_rows != ix->ntotal;
+    struct NormGuard {  // the scan launches of THIS search normalise their queries while staging them
+        b200_index* ix;
+        ~NormGuard() { ix->cur_norm_q = false; }
+    } norm_guard{ix};
+    if (ix->opt_normalize_queries) {
+        if (ix->opt_fuse_query_norm && !use_gemm) {
+            ix->cur_norm_q = true;
+        } else {  // the tensor-core path builds its bf16 query shadow from normalised queries in memory
+            if (ix->qn_cap < (size_t)nq * ix->d) {
+                CK(cudaStreamSynchronize(st));
+                CKI(grow(&ix->qn_dev, &ix->qn_cap, (size_t)nq * ix->d));
+            }
+            CKI(ingest_dev(ix->d, ix->d, B200_STORE_F32, q_dev, (uint8_t*)ix->qn_dev, (size_t)ix->d * 4, nq, 1,
+                           ix->num_sms, st, &ix->launches));
+            q_dev = ix->qn_dev;
+        }
+    }
     ix->stat_gemm_used = 0;
     if (!fullrank) {
-        if (!ix->xchg_active && gemm_eligible(ix, nq, k) && ix->sh_failed_rows != ix->ntotal) {
+        if (use_gemm) {
             // K3 in blocks of at most 16384 queries (bounds the candidate scratch)
             int rc = 0;
             for (int64_t q0 = 0; q0 < nq && rc == 0; q0 += 16384) {
@@ -1882,16 +2001,42 @@ extern "C" int b200_index_search_exchange_dev(b200_index* ix, const float* q_dev
     if (k > B200_FUSED_K_MAX || k >= ix->opt_fullrank_min_k) return fail("fused exchange needs k <= %d", B200_FUSED_K_MAX);
     if (ix->ntotal == 0) return fail("fused exchange needs at least one row on every rank");
     if (*ix->xchg_status_host) return fail("fused exchange: a peer GPU did not deliver its results in time during an earlier search");
+    if ((int64_t)ix->xchg_world * std::min<int64_t>(nq, 8) * k > XCHG_MAX_ENTRIES)
+        return fail("fused exchange: world x queries x k exceeds %d entries", XCHG_MAX_ENTRIES);
     ix->xchg_active = true;
     int rc = b200_index_search_dev(ix, q_dev, nq, k, D_dev, I_dev, stream);
     ix->xchg_active = false;
     return rc;
 }
 
+// 0 = every fused exchange so far completed; 1 = a peer did not deliver in time (the affected search returned
+// padding only).  Read it after synchronising the stream the search ran on.
+extern "C" int b200_index_exchange_status(b200_index* ix) {
+    if (!ix) return -1;
+    return ix->xchg_status_host ? *ix->xchg_status_host : 0;
+}
+
+// Phase stamps (globaltimer, ns) of the last scan launch made with option scan_phase_stamps = 1:
+// out[cta * 8 + j], j = 0 kernel entry, 1 queries staged, 2 scan done (warp 0), 3 CTA reduction written, 4 last CTA
+// starts the final merge, 5 final merge done, 6 kernel end (last CTA), 7 first tile landed (warp 0); 0 = not reached.
+extern "C" int b200_index_read_phase_stamps(b200_index* ix, unsigned long long* out_host, int64_t cap_words, int64_t* n_ctas) {
+    if (!ix || !out_host || !n_ctas) return fail("null argument");
+    *n_ctas = 0;
+    if (!ix->stamps || ix->stamps_grid == 0) return fail("no phase stamps recorded (set option scan_phase_stamps)");
+    if (cap_words < (int64_t)ix->stamps_grid * 8) return fail("buffer too small for %d CTAs", ix->stamps_grid);
+    CKI(use_device(ix));
+    cudaStream_t st = ix->last_stream ? ix->last_stream : ix->stream;
+    CK(cudaMemcpyAsync(out_host, ix->stamps, (size_t)ix->stamps_grid * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_ctas = ix->stamps_grid;
+    return 0;
+}
+
 extern "C" int64_t b200_index_launch_count(b200_index* ix) { return ix ? ix->launches : -1; }
 extern "C" int b200_index_sync(b200_index* ix) {
     if (!ix) return fail("null index");
     CKI(use_device(ix));
+    CKI(order_after_previous_stream(ix, ix->stream));
     CK(cudaStreamSynchronize(ix->stream));
     return 0;
 }

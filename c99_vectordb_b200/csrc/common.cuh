@@ -140,6 +140,14 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                  : "l"(p));
     return r;
 }
+// Programmatic dependent launch (no-ops in a kernel launched without the attribute).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ float warp_sum_xor(float v) {
     v += __shfl_xor_sync(B200_FULL_MASK, v, 16);
     v += __shfl_xor_sync(B200_FULL_MASK, v, 8);

@@ -9,9 +9,12 @@
 #pragma once
 #include "common.cuh"
 
+// Padding entries (a shard with fewer than k candidates) carry the sentinel score -/+FLT_MAX, which no candidate can
+// have; they are recognised by it, not by a negative id — negative record ids are legal in an id map.
 template <int METRIC>
 __device__ __forceinline__ uint32_t merge_hi(float s, int64_t id) {
-    return (id < 0) ? 0u : b200_key_hi<METRIC>(s);
+    (void)id;
+    return b200_score_valid<METRIC>(s) ? b200_key_hi<METRIC>(s) : 0u;
 }
 
 // lists are descending in hi.  number of entries with hi > h (strict) or hi >= h
@@ -54,8 +57,8 @@ merge_topk_kernel(int G, int64_t nq, int64_t k, const float* __restrict__ Dp,
             rank += count_better<METRIC>(D2, I2, k, h, /*or_equal=*/g2 < g);
         }
         if (rank < k) {
-            Do[q * k + rank] = (id < 0) ? ((METRIC == 0) ? -FLT_MAX : FLT_MAX) : s;
-            Io[q * k + rank] = (id < 0) ? (int64_t)-1 : id;
+            Do[q * k + rank] = h == 0u ? ((METRIC == 0) ? -FLT_MAX : FLT_MAX) : s;
+            Io[q * k + rank] = h == 0u ? (int64_t)-1 : id;
         }
     }
 }

@@ -19,11 +19,22 @@
 // Top-k: per warp an unsorted k-entry list of 64-bit keys in shared memory plus the running
 // threshold tau = worst key kept; a row is inserted only when its key beats tau (rare after
 // warm-up: ~k*ln(rows_per_warp/k) inserts per warp per scan).  At the end of the scan the CTA
-// bitonic-sorts its warps' lists, writes its best k keys, and the LAST CTA to finish (atomic
-// ticket) merges all CTA partials, translates row -> record id (K5) and writes D/I — so a search
-// is a single launch.  On a sharded index the same tail also exchanges the result with the peer
-// GPUs over NVLink and merges (exchange_and_merge).  Tiles are claimed in ascending runs from a
-// global counter (dynamic scheduler) unless p.dynamic == 0.
+// keeps the keys that can still matter (>= the best k-th key of its warps: that warp alone proves
+// k better-or-equal candidates), writes them unsorted together with their count, and raises the
+// launch's global threshold (atomicMax); the LAST CTA to finish (atomic ticket) reads every CTA's
+// survivors in one pass, drops what is below the global threshold, sorts the few dozen keys that
+// remain, translates row -> record id (K5) and writes D/I — so a search is a single launch and its
+// tail is three L2 round trips.  On a sharded index the same tail also exchanges the result with
+// the peer GPUs over NVLink and merges (exchange_and_merge).  Tiles are claimed in ascending runs
+// from a global counter whose run length shrinks towards the end of the database (guided
+// self-scheduling) unless p.dynamic == 0.
+//
+// Programmatic dependent launch (p.pdl): back-to-back searches on one stream overlap — the next
+// launch's CTAs take over SMs as this launch's CTAs exit, so its ramp-up (and, when the caller
+// promises stable queries, its whole scan) hides this launch's merge + exchange.  Per-launch
+// control words (ticket, tile counter, thresholds, survivor lists) are double-buffered by launch
+// parity; every CTA executes griddepcontrol.wait before it signals launch_dependents, so launch
+// i+2 cannot start before launch i has completed.
 #pragma once
 #include "common.cuh"
 
@@ -34,6 +45,7 @@
 #define B200_SCAN_THREADS_LDG 256   // direct-load variant: 4 CTAs of 8 warps per SM (<= 64 registers)
 #define B200_FUSED_K_MAX 256
 #define B200_FINAL_BUF_KEYS 2048
+#define B200_PREF_BYTES 4096u       // prefix sums of the per-CTA survivor counts: grids of up to 1023 CTAs
 
 struct ScanParams {
     const uint8_t* rows;      // row storage
@@ -45,10 +57,18 @@ struct ScanParams {
     int qstride;              // padded floats per query in shared memory (multiple of 8)
     int nqb;                  // queries in this launch (<= QB)
     int k;                    // results per query (top-k mode)
-    uint64_t* partials;       // [grid, QB, k] per-CTA best keys
+    uint64_t* partials;       // [grid, QB, part_cap] per-CTA surviving keys (unsorted)
+    unsigned int* part_count; // [grid, QB] number of surviving keys per CTA and query
+    uint32_t part_cap;        // warps * k
+    unsigned long long* gtau; // [QB] global threshold of this launch: max over CTAs of their best k-th key (0 = none yet)
     unsigned int* ticket;     // [0] CTA-done ticket, [1] tile counter; zero before launch, reset by the last CTA
     int dynamic;              // 1: tiles claimed in order from the global counter; 0: static striding
-    uint32_t claim_chunk;     // dynamic: consecutive tiles taken per atomic claim (>= 1)
+    uint32_t claim_chunk;     // dynamic: most consecutive tiles taken per atomic claim (>= 1)
+    uint32_t claim_min;       // dynamic: fewest (the run shrinks with the tiles that remain)
+    int pdl;                  // 0: plain launch; 1: launched with programmatic stream serialisation, queries may come
+                              // from the preceding kernel (wait before reading them); 2: queries are stable (wait after the scan)
+    int normalize_q;          // 1: L2-normalise the queries while staging them (K1 arithmetic, memo_cli.py:131-135)
+    unsigned long long* stamps;  // optional [grid, 8] globaltimer stamps of the phases (null = off)
     int fused_tail;           // 1: the last CTA does the final merge; 0: final_merge_kernel follows
     float* D;                 // [nqb, k] out
     int64_t* I;               // [nqb, k] out
@@ -67,7 +87,7 @@ struct ScanParams {
     uint32_t xchg_epoch;      // strictly increasing per launch
     uint32_t xchg_slot_bytes; // bytes of one (parity, sender) slot
     int* xchg_status;         // set to 1 if a peer never showed up
-    uint32_t scratch_keys;    // power of two >= max(warps*k, B200_FINAL_BUF_KEYS)
+    uint32_t scratch_keys;    // B200_FINAL_BUF_KEYS (power of two >= 2k)
 };
 
 // ---- small device pieces ---------------------------------------------------------------------
@@ -147,83 +167,84 @@ __device__ __forceinline__ void cta_bitonic_sort_desc(uint64_t* a, uint32_t m) {
     __syncthreads();
 }
 
-// Merge the per-CTA partial lists of query qi (nctas lists of k keys, each best-first) into the
-// final result, translate row -> record id (K5) and write D/I.  Whole CTA.  scratch[0..k) holds
-// the running best (sorted); whole CTA lists are appended behind it — unfiltered and without
-// atomics while no threshold exists yet, filtered against the running k-th best afterwards — and
-// the buffer is re-sorted when it fills up.
+// Final merge of query qi by the whole CTA: every CTA left part_count[cta] surviving keys (unsorted, each >= that
+// CTA's own threshold); keys below the launch's global threshold gtau cannot be among the best k (some warp holds k
+// keys >= gtau), so typically only k + a few dozen keys pass the filter.  They are collected in `scratch` (B keys) in
+// ONE pass over all CTAs — a window of the flat survivor sequence never holds more keys than the buffer has room for —
+// sorted, and the first k are translated row -> record id (K5) and written.  Adversarial inputs (thousands of keys
+// above the threshold) take further windows, re-sorting and tightening the threshold between them.
+// s_pref: nctas + 1 words of shared memory (exclusive prefix sums of the counts).
 template <int METRIC, int QB>
 __device__ __forceinline__ void final_merge_one(const ScanParams& p, int qi, uint32_t nctas, uint64_t* scratch,
-                                                unsigned int* sctr) {
+                                                unsigned int* sctr, uint32_t* s_pref) {
     const int k = p.k;
     const uint32_t B = p.scratch_keys;
-    for (uint32_t i = threadIdx.x; i < B; i += blockDim.x) scratch[i] = 0ull;
-    if (threadIdx.x == 0) *sctr = (unsigned)k;
-    // Pre-filter: a CTA whose list is full proves that k candidates are at least as good as its k-th
-    // key, so the global k-th best cannot be below tau0 = max over CTAs of their k-th keys.  Typically
-    // only a few dozen of the nctas*k keys survive, so the sort below handles 32-128 keys, not 2048.
-    __shared__ unsigned long long s_tau0;
-    if (threadIdx.x == 0) s_tau0 = 0ull;
     __syncthreads();
-    {
-        uint64_t t0 = 0ull;
-        for (uint32_t c = threadIdx.x; c < nctas; c += blockDim.x) {
-            uint64_t kth = __ldcg(p.partials + ((size_t)c * QB + qi) * k + (k - 1));
-            t0 = kth > t0 ? kth : t0;
-        }
+    for (uint32_t c = threadIdx.x; c < nctas; c += blockDim.x) s_pref[c + 1] = __ldcg(p.part_count + (size_t)c * QB + qi);
+    if (threadIdx.x == 0) {
+        s_pref[0] = 0u;
+        *sctr = 0u;
+    }
+    const unsigned long long g = __ldcg(p.gtau + qi);
+    uint64_t thr = g ? (uint64_t)g - 1ull : 0ull;  // keep key > thr  <=>  key >= gtau (any non-empty key when no list was full)
+    __syncthreads();
+    if (threadIdx.x < 32) {  // inclusive scan of the counts by one warp
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < nctas; base += 32) {
+            const uint32_t i = base + threadIdx.x;
+            uint32_t v = i < nctas ? s_pref[i + 1] : 0u;
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            uint64_t o = __shfl_xor_sync(B200_FULL_MASK, t0, m);
-            t0 = o > t0 ? o : t0;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(B200_FULL_MASK, v, o);
+                if ((int)threadIdx.x >= o) v += u;
+            }
+            if (i < nctas) s_pref[i + 1] = v + carry;
+            carry += __shfl_sync(B200_FULL_MASK, v, 31);
         }
-        if ((threadIdx.x & 31) == 0 && t0) atomicMax(&s_tau0, (unsigned long long)t0);
     }
     __syncthreads();
-    const uint64_t tau0 = s_tau0 ? (uint64_t)s_tau0 - 1ull : 0ull;  // keep keys >= max k-th key
-    uint32_t cta = 0;
-    while (cta < nctas) {
-        uint32_t filled = *sctr;
-        uint32_t fit = (B - filled) / (uint32_t)k;  // whole lists that fit (B >= 2k by construction)
-        if (fit == 0) fit = 1;
-        uint32_t take = nctas - cta < fit ? nctas - cta : fit;
-        uint64_t tau_now = scratch[k - 1];
-        if (tau0 > tau_now) tau_now = tau0;
-        __syncthreads();
-        if (tau_now == 0ull) {
-            for (uint32_t i = threadIdx.x; i < take * (uint32_t)k; i += blockDim.x) {
-                uint32_t c = cta + i / k, j = i % k;
-                scratch[filled + i] = __ldcg(p.partials + ((size_t)c * QB + qi) * k + j);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) *sctr = filled + take * (uint32_t)k;
-        } else {
-            for (uint32_t i = threadIdx.x; i < take * (uint32_t)k; i += blockDim.x) {
-                uint32_t c = cta + i / k, j = i % k;
-                uint64_t key = __ldcg(p.partials + ((size_t)c * QB + qi) * k + j);
-                if (key > tau_now) {
-                    unsigned slot = atomicAdd(sctr, 1u);
-                    scratch[slot] = key;
+    const uint32_t total = s_pref[nctas];
+    uint32_t pos = 0, filled = 0;
+    do {
+        const uint32_t room = B - filled;
+        const uint32_t end = total - pos < room ? total : pos + room;
+        constexpr int U = 4;  // loads in flight per thread
+        for (uint32_t i0 = pos + threadIdx.x; i0 < end; i0 += blockDim.x * U) {
+            uint64_t key[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+                key[u] = 0ull;
+                if (i < end) {
+                    uint32_t lo = 0, hi = nctas;  // the CTA whose range [pref[c], pref[c+1]) holds item i
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (s_pref[mid] <= i) lo = mid; else hi = mid;
+                    }
+                    key[u] = __ldcg(p.partials + ((size_t)lo * QB + qi) * p.part_cap + (i - s_pref[lo]));
                 }
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (key[u] > thr) scratch[atomicAdd(sctr, 1u)] = key[u];
         }
-        cta += take;
+        pos = end;
         __syncthreads();
         filled = *sctr;
-        bool last_round = (cta >= nctas);
-        bool full = (B - filled) < (uint32_t)k;
-        if (last_round || full) {
-            uint32_t mm = 2;
-            while (mm < filled) mm <<= 1;
-            for (uint32_t i = filled + threadIdx.x; i < mm; i += blockDim.x) scratch[i] = 0ull;
-            cta_bitonic_sort_desc(scratch, mm);
-            for (uint32_t i = (uint32_t)k + threadIdx.x; i < mm; i += blockDim.x) scratch[i] = 0ull;
+        uint32_t mm = 2;
+        while (mm < filled) mm <<= 1;
+        for (uint32_t i = filled + threadIdx.x; i < mm; i += blockDim.x) scratch[i] = 0ull;
+        cta_bitonic_sort_desc(scratch, mm);
+        if (filled > (uint32_t)k) filled = (uint32_t)k;
+        if (pos < total) {  // more windows: the k-th best so far is the new threshold (keys are unique)
+            if (filled == (uint32_t)k && scratch[k - 1] > thr) thr = scratch[k - 1];
             __syncthreads();
-            if (threadIdx.x == 0) *sctr = (unsigned)k;
+            if (threadIdx.x == 0) *sctr = filled;
             __syncthreads();
         }
-    }
+    } while (pos < total);
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        uint64_t key = scratch[i];
+        const uint64_t key = (uint32_t)i < filled ? scratch[i] : 0ull;
         float dist;
         int64_t id;
         if (key == 0ull) {
@@ -235,15 +256,20 @@ __device__ __forceinline__ void final_merge_one(const ScanParams& p, int qi, uin
             id = p.id_map ? p.id_map[row] : (int64_t)row + p.id_base;
         }
         if (p.xchg_peers) {
-            // the local result goes straight into slot [parity][my rank] of EVERY rank's exchange
-            // buffer: posted stores over NVLink (and a plain store for the own buffer)
+            // The local result goes straight into slot [parity][my rank] of EVERY rank's exchange buffer as three
+            // self-validating 8-byte words per entry (value, epoch) — 8-byte stores are single transactions, so the
+            // receiver needs no fence and no separate flag: a word whose upper half carries this launch's epoch is
+            // complete.  Posted stores over NVLink (a plain store for the own buffer).
             const size_t slot = ((size_t)(p.xchg_epoch & 1u) * p.xchg_world + p.xchg_rank) * p.xchg_slot_bytes;
-            const size_t off_i = 16 + ((size_t)qi * k + i) * 8;
-            const size_t off_d = 16 + (size_t)p.nqb * k * 8 + ((size_t)qi * k + i) * 4;
-            for (int g = 0; g < p.xchg_world; ++g) {
-                uint8_t* base = p.xchg_peers[g] + slot;
-                *reinterpret_cast<int64_t*>(base + off_i) = id;
-                *reinterpret_cast<float*>(base + off_d) = dist;
+            const size_t off = 16 + ((size_t)qi * k + i) * 24;
+            const uint64_t ep = (uint64_t)p.xchg_epoch << 32;
+            const uint64_t w0 = ep | (uint32_t)((uint64_t)id & 0xffffffffull), w1 = ep | (uint32_t)((uint64_t)id >> 32),
+                           w2 = ep | __float_as_uint(dist);
+            for (int gg = 0; gg < p.xchg_world; ++gg) {
+                uint64_t* dst = reinterpret_cast<uint64_t*>(p.xchg_peers[(gg + p.xchg_rank) % p.xchg_world] + slot + off);
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(w0) : "memory");
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(w1) : "memory");
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 2), "l"(w2) : "memory");
             }
         } else {
             p.D[(size_t)qi * k + i] = dist;
@@ -253,61 +279,87 @@ __device__ __forceinline__ void final_merge_one(const ScanParams& p, int qi, uin
     __syncthreads();
 }
 
-// Fused multi-GPU top-k exchange, run by the last CTA of every rank's scan kernel after its local
-// results have been stored into all peers' buffers: publish (release, system scope) an epoch flag
-// in every peer's slot header, wait until all world flags of the OWN buffer carry this epoch, then
-// merge the world best-first lists per query with the K4 rank-by-counting rule (score best-first,
-// lower rank first, earlier position first) and write the final D/I.  Slots are double-buffered by
-// epoch parity: a rank cannot be two searches ahead of a peer because each search needs every
-// peer's flag.  Kernels on DIFFERENT GPUs wait on one another here — never two kernels of one GPU.
+// Fused multi-GPU top-k exchange, run by the last CTA of every rank's scan kernel after its local results have been
+// posted into all peers' buffers: wait until every word of the world lists in the OWN buffer carries this launch's
+// epoch, then merge the world best-first lists per query with the K4 rank-by-counting rule (score best-first, lower
+// rank first, earlier position first) out of shared memory and write the final D/I.  Slots are double-buffered by
+// epoch parity: a rank cannot be two searches ahead of a peer because each search needs every peer's entries.
+// Kernels on DIFFERENT GPUs wait on one another here — never two kernels of one GPU.  A peer that does not deliver
+// within ~2 s marks the launch failed: every result is padding (-1) and *xchg_status is set.
+// Padding entries are recognised by their sentinel score, not by a negative id (negative record ids are legal).
+// s_h: world * nqb * k words of shared memory.
 template <int METRIC>
-__device__ __forceinline__ void exchange_and_merge(const ScanParams& p) {
+__device__ __forceinline__ void exchange_and_merge(const ScanParams& p, uint32_t* s_h) {
     const int k = p.k, G = p.xchg_world;
-    const size_t parity_base = (size_t)(p.xchg_epoch & 1u) * G * p.xchg_slot_bytes;
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < G) {
-        uint32_t* flag = reinterpret_cast<uint32_t*>(p.xchg_peers[threadIdx.x] + parity_base + (size_t)p.xchg_rank * p.xchg_slot_bytes);
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(p.xchg_epoch) : "memory");
-        const uint32_t* mine = reinterpret_cast<const uint32_t*>(p.xchg_peers[p.xchg_rank] + parity_base + (size_t)threadIdx.x * p.xchg_slot_bytes);
-        const long long t0 = clock64();
-        uint32_t v;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-            if (v != p.xchg_epoch && clock64() - t0 > 20000000000ll) {  // ~10 s: a peer is gone
-                *p.xchg_status = 1;
+    const uint8_t* own = p.xchg_peers[p.xchg_rank] + (size_t)(p.xchg_epoch & 1u) * G * p.xchg_slot_bytes;
+    const int total = G * p.nqb * k;
+    auto words_of = [&](int t) {  // entry t enumerates (q, g, j)
+        const int q = t / (G * k), r = t - q * (G * k), g = r / k, j = r - g * k;
+        return reinterpret_cast<const uint64_t*>(own + (size_t)g * p.xchg_slot_bytes + 16 + ((size_t)q * k + j) * 24);
+    };
+    int64_t id0 = -1;
+    float sc0 = 0.0f;
+    int timed_out = 0;
+    const long long t0 = clock64();
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        const uint64_t* w = words_of(t);
+        uint64_t w0, w1, w2;
+        for (;;) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w0) : "l"(w) : "memory");
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w1) : "l"(w + 1) : "memory");
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w2) : "l"(w + 2) : "memory");
+            if ((uint32_t)(w0 >> 32) == p.xchg_epoch && (uint32_t)(w1 >> 32) == p.xchg_epoch && (uint32_t)(w2 >> 32) == p.xchg_epoch) break;
+            if (clock64() - t0 > 4000000000ll) {  // ~2 s: a peer is gone
+                timed_out = 1;
                 break;
             }
-        } while (v != p.xchg_epoch);
+        }
+        const float sc = __uint_as_float((uint32_t)w2);
+        s_h[t] = (timed_out || !b200_score_valid<METRIC>(sc)) ? 0u : b200_key_hi<METRIC>(sc);
+        if (t == (int)threadIdx.x) {
+            id0 = (int64_t)((w0 & 0xffffffffull) | (w1 << 32));
+            sc0 = sc;
+        }
     }
-    __syncthreads();
-    const uint8_t* own = p.xchg_peers[p.xchg_rank] + parity_base;
-    const int total = G * p.nqb * k;
+    const int failed = __syncthreads_or(timed_out);
+    if (failed) {
+        if (threadIdx.x == 0) *p.xchg_status = 1;
+        for (int t = threadIdx.x; t < p.nqb * k; t += blockDim.x) {
+            p.D[t] = (METRIC == 0) ? -FLT_MAX : FLT_MAX;
+            p.I[t] = -1;
+        }
+        return;
+    }
     for (int t = threadIdx.x; t < total; t += blockDim.x) {
         const int q = t / (G * k), r = t - q * (G * k), g = r / k, j = r - g * k;
-        auto Iof = [&](int gg) { return reinterpret_cast<const int64_t*>(own + (size_t)gg * p.xchg_slot_bytes + 16) + (size_t)q * k; };
-        auto Dof = [&](int gg) { return reinterpret_cast<const float*>(own + (size_t)gg * p.xchg_slot_bytes + 16 + (size_t)p.nqb * k * 8) + (size_t)q * k; };
-        const int64_t id = __ldcv(Iof(g) + j);
-        const float sc = __ldcv(Dof(g) + j);
-        const uint32_t h = id < 0 ? 0u : b200_key_hi<METRIC>(sc);
+        int64_t id = id0;
+        float sc = sc0;
+        if (t != (int)threadIdx.x) {  // entries beyond the first sweep: read them again (they have arrived)
+            const uint64_t* w = words_of(t);
+            uint64_t w0, w1, w2;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w0) : "l"(w) : "memory");
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w1) : "l"(w + 1) : "memory");
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w2) : "l"(w + 2) : "memory");
+            id = (int64_t)((w0 & 0xffffffffull) | (w1 << 32));
+            sc = __uint_as_float((uint32_t)w2);
+        }
+        const uint32_t h = s_h[t];
         int rank = j;
         for (int g2 = 0; g2 < G; ++g2) {
             if (g2 == g) continue;
-            const int64_t* I2 = Iof(g2);
-            const float* D2 = Dof(g2);
+            const uint32_t* H2 = s_h + ((size_t)q * G + g2) * k;
             int lo = 0, hi = k;  // entries of list g2 that precede this candidate
             while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                int64_t im = __ldcv(I2 + mid);
-                uint32_t hm = im < 0 ? 0u : b200_key_hi<METRIC>(__ldcv(D2 + mid));
-                bool before = (g2 < g) ? (hm >= h) : (hm > h);
+                const int mid = (lo + hi) >> 1;
+                const uint32_t hm = H2[mid];
+                const bool before = (g2 < g) ? (hm >= h) : (hm > h);
                 if (before) lo = mid + 1; else hi = mid;
             }
             rank += lo;
         }
         if (rank < k) {
-            p.D[(size_t)q * k + rank] = id < 0 ? ((METRIC == 0) ? -FLT_MAX : FLT_MAX) : sc;
-            p.I[(size_t)q * k + rank] = id < 0 ? (int64_t)-1 : id;
+            p.D[(size_t)q * k + rank] = h == 0u ? ((METRIC == 0) ? -FLT_MAX : FLT_MAX) : sc;
+            p.I[(size_t)q * k + rank] = h == 0u ? (int64_t)-1 : id;
         }
     }
 }
@@ -319,7 +371,9 @@ __global__ void __launch_bounds__(256) final_merge_kernel(const ScanParams p, ui
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* scratch = reinterpret_cast<uint64_t*>(smem);
     unsigned int* sctr = reinterpret_cast<unsigned int*>(smem + (size_t)p.scratch_keys * 8);
-    final_merge_one<METRIC, QB>(p, blockIdx.x, nctas, scratch, sctr);
+    uint32_t* s_pref = reinterpret_cast<uint32_t*>(sctr + 4);
+    final_merge_one<METRIC, QB>(p, blockIdx.x, nctas, scratch, sctr, s_pref);
+    if (threadIdx.x == 0) p.gtau[blockIdx.x] = 0ull;  // ready for the launch after next (same parity set)
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
@@ -344,25 +398,23 @@ scan_topk_kernel(const ScanParams p) {
     // ---- shared memory carve-up (host computes the same sizes: scan_smem_bytes) ----
     // [ring: nw*stages*tile_bytes | scratch (aliases ring start)] [queries] [lists] [mbarriers] [ctr] [stage tiles]
     uint32_t ring_bytes = (VARIANT == B200_VARIANT_BULK) ? nw * p.stages * p.tile_bytes : 0u;
-    uint32_t scratch_bytes = p.scratch_keys * 8u;
+    uint32_t scratch_bytes = p.scratch_keys * 8u + B200_PREF_BYTES;  // final-merge buffer + per-CTA count prefix sums
     uint32_t region0 = ring_bytes > scratch_bytes ? ring_bytes : scratch_bytes;
     region0 = (region0 + 127u) & ~127u;
     uint8_t* ring = smem;
     uint64_t* scratch = reinterpret_cast<uint64_t*>(smem);
+    uint32_t* s_pref = reinterpret_cast<uint32_t*>(smem + p.scratch_keys * 8u);
     float* qs = reinterpret_cast<float*>(smem + region0);
     uint32_t q_bytes = (uint32_t)QB * p.qstride * 4u;
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + region0 + q_bytes);
     uint32_t list_bytes = fullrank ? 0u : (uint32_t)nw * QB * k * 8u;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + region0 + q_bytes + list_bytes);
     unsigned int* sctr = reinterpret_cast<unsigned int*>(bars + nw * (VARIANT == B200_VARIANT_BULK ? p.stages : 0u));
-    uint32_t* stage_tile = reinterpret_cast<uint32_t*>(sctr + 4) + warp * (VARIANT == B200_VARIANT_BULK ? p.stages : 0u);
+    uint32_t* stage_tile = reinterpret_cast<uint32_t*>(sctr + 16) + warp * (VARIANT == B200_VARIANT_BULK ? p.stages : 0u);
     __shared__ unsigned int s_is_last;
 
-    // ---- stage queries (zero padded) and clear lists ----
-    for (int i = threadIdx.x; i < QB * p.qstride; i += blockDim.x) {
-        int qi = i / p.qstride, c = i - qi * p.qstride;
-        qs[i] = (qi < p.nqb && c < p.d) ? p.q[(size_t)qi * p.d + c] : 0.0f;
-    }
+    if (p.stamps && threadIdx.x == 0) p.stamps[blockIdx.x * 8 + 0] = globaltimer_ns();
+    // ---- clear lists (the queries are staged below, after the first tiles have been requested) ----
     if (!fullrank)
         for (int i = threadIdx.x; i < nw * QB * k; i += blockDim.x) lists[i] = 0ull;
 
@@ -376,11 +428,19 @@ scan_topk_kernel(const ScanParams p) {
     uint32_t static_next = blockIdx.x * nw + warp;
     const uint32_t static_step = gridDim.x * nw;
     uint32_t chunk_next = 0, chunk_end = 0;  // lane 0: the claimed run of consecutive tiles
+    const uint32_t guide_div = 2u * gridDim.x * (uint32_t)nw;
     auto claim = [&]() -> uint32_t {  // called by lane 0 only
         if (p.dynamic) {
-            if (chunk_next == chunk_end) {  // one atomic per claim_chunk tiles (a single hot address
-                chunk_next = atomicAdd(p.ticket + 1, p.claim_chunk);  // serialises at ~2.5 ns/op)
-                chunk_end = chunk_next + p.claim_chunk;
+            if (chunk_next == chunk_end) {
+                // One atomic per run of tiles (a single hot address serialises at ~2.5 ns/op).  Guided
+                // self-scheduling: the run is 1/(2 x warps) of what was left at this warp's previous claim,
+                // between claim_min and claim_chunk tiles, so the warps run out of work within claim_min tiles
+                // of one another instead of claim_chunk.
+                const uint32_t left = chunk_end < tiles_total ? tiles_total - chunk_end : 0u;
+                uint32_t run = left / guide_div;
+                run = run < p.claim_min ? p.claim_min : (run > p.claim_chunk ? p.claim_chunk : run);
+                chunk_next = atomicAdd(p.ticket + 1, run);
+                chunk_end = chunk_next + run;
             }
             return chunk_next++;
         }
@@ -438,6 +498,42 @@ scan_topk_kernel(const ScanParams p) {
         t_cur = __shfl_sync(B200_FULL_MASK, t_cur, 0);
     }
 
+    // ---- stage the queries (zero padded; optionally L2-normalised with K1's arithmetic) ----
+    // With programmatic dependent launch everything above (and the first tiles in flight) overlapped the
+    // previous kernel's tail; the queries may be its output unless the caller promised otherwise.
+    if (p.pdl == 1) {
+        griddep_wait();
+        griddep_launch_dependents();
+    }
+    if (p.normalize_q) {
+        const int nchunk = (p.d + 3) >> 2;
+        for (int qi = warp; qi < QB; qi += nw) {
+            float* dst = qs + (size_t)qi * p.qstride;
+            if (qi >= p.nqb) {
+                for (int c = lane; c < p.qstride; c += 32) dst[c] = 0.0f;
+                continue;
+            }
+            const float* src = p.q + (size_t)qi * p.d;
+            float acc = 0.0f;  // lane l owns the 4-element chunks l, l+32, ...: ingest_rows_kernel's order
+            for (int c = lane; c < nchunk; c += 32)
+                for (int e = 4 * c; e < 4 * c + 4 && e < p.d; ++e) {
+                    const float v = src[e];
+                    acc = fmaf(v, v, acc);
+                }
+            acc = warp_sum_xor(acc);
+            const float nrm = __fsqrt_rn(acc);
+            const bool zero = ((double)nrm <= 1e-8);  // memo_cli.py:133 compares against the double 1e-8
+            for (int c = lane; c < p.qstride; c += 32) dst[c] = (c < p.d && !zero) ? __fdiv_rn(src[c], nrm) : 0.0f;
+        }
+    } else {
+        for (int i = threadIdx.x; i < QB * p.qstride; i += blockDim.x) {
+            int qi = i / p.qstride, c = i - qi * p.qstride;
+            qs[i] = (qi < p.nqb && c < p.d) ? p.q[(size_t)qi * p.d + c] : 0.0f;
+        }
+    }
+    __syncthreads();
+    if (p.stamps && threadIdx.x == 0) p.stamps[blockIdx.x * 8 + 1] = globaltimer_ns();
+
     uint64_t tau[QB];
     int tau_pos[QB];
 #pragma unroll
@@ -460,6 +556,7 @@ scan_topk_kernel(const ScanParams p) {
             if (t == NOTILE) break;
             uint32_t parity = (it / p.stages) & 1u;
             mbar_wait(bar0 + 8u * s, parity);
+            if (p.stamps && it == 0 && threadIdx.x == 0) p.stamps[blockIdx.x * 8 + 7] = globaltimer_ns();
             tile_smem = ring + ((size_t)warp * p.stages + s) * p.tile_bytes;
         } else {
             t = t_cur;
@@ -597,26 +694,42 @@ scan_topk_kernel(const ScanParams p) {
         }
     }
 
-    // ---- CTA merge: the warps' lists -> this CTA's best k per query ----
+    if (p.stamps && threadIdx.x == 0) p.stamps[blockIdx.x * 8 + 2] = globaltimer_ns();
+    // ---- CTA reduction: keep the keys that can still be among the best k, unsorted ----
+    // tau of a warp is its k-th best key once its list is full (0 before): that warp alone proves k candidates
+    // >= tau, so nothing below the best warp threshold of this CTA can matter.
+    unsigned long long* s_tau = reinterpret_cast<unsigned long long*>(scratch);  // [nw, QB] (the ring has been consumed)
     __syncthreads();  // all warps done; every issued bulk copy has been consumed
-    uint32_t m = 2;
-    while (m < (uint32_t)(nw * k)) m <<= 1;
-    for (int qi = 0; qi < (fullrank ? 0 : p.nqb); ++qi) {
-        for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-            uint64_t v = 0ull;
-            if (i < (uint32_t)(nw * k)) {
-                uint32_t w = i / k, j = i - w * k;
-                v = lists[((size_t)w * QB + qi) * k + j];
-            }
-            scratch[i] = v;
-        }
-        cta_bitonic_sort_desc(scratch, m);
-        uint64_t* out = p.partials + ((size_t)blockIdx.x * QB + qi) * k;
-        for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = scratch[i];
-        __syncthreads();
+    if (p.pdl == 2) {  // stable queries: this launch only has to be ordered behind the previous one from here on
+        griddep_wait();
+        griddep_launch_dependents();
     }
+    if (!fullrank) {
+        if (lane == 0)
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) s_tau[warp * QB + qi] = tau[qi];
+        if (threadIdx.x < QB) sctr[threadIdx.x] = 0u;
+        __syncthreads();
+        for (int qi = 0; qi < p.nqb; ++qi) {
+            unsigned long long t = 0ull;
+            for (int w = 0; w < nw; ++w) {
+                const unsigned long long v = s_tau[w * QB + qi];
+                t = v > t ? v : t;
+            }
+            uint64_t* out = p.partials + ((size_t)blockIdx.x * QB + qi) * p.part_cap;
+            for (int i = threadIdx.x; i < nw * k; i += blockDim.x) {
+                const int w = i / k, j = i - w * k;
+                const uint64_t key = lists[((size_t)w * QB + qi) * k + j];
+                if (key != 0ull && key >= t) out[atomicAdd(sctr + qi, 1u)] = key;
+            }
+            if (threadIdx.x == 0 && t) atomicMax(p.gtau + qi, t);
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < p.nqb) p.part_count[(size_t)blockIdx.x * QB + threadIdx.x] = sctr[threadIdx.x];
+    }
+    if (p.stamps && threadIdx.x == 0) p.stamps[blockIdx.x * 8 + 3] = globaltimer_ns();
 
-    // ---- last CTA: merge all partials, translate ids, write D/I ----
+    // ---- last CTA: merge all survivors, translate ids, write D/I ----
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -626,13 +739,17 @@ scan_topk_kernel(const ScanParams p) {
     __syncthreads();
     if (!s_is_last) return;
     __threadfence();
+    if (p.stamps && threadIdx.x == 0) p.stamps[blockIdx.x * 8 + 4] = globaltimer_ns();
     if (!fullrank && p.fused_tail) {
-        for (int qi = 0; qi < p.nqb; ++qi) final_merge_one<METRIC, QB>(p, qi, gridDim.x, scratch, sctr);
-        if (p.xchg_peers) exchange_and_merge<METRIC>(p);
+        for (int qi = 0; qi < p.nqb; ++qi) final_merge_one<METRIC, QB>(p, qi, gridDim.x, scratch, sctr + QB, s_pref);
+        if (p.stamps && threadIdx.x == 0) p.stamps[blockIdx.x * 8 + 5] = globaltimer_ns();
+        if (p.xchg_peers) exchange_and_merge<METRIC>(p, reinterpret_cast<uint32_t*>(scratch));
+        if ((int)threadIdx.x < p.nqb) p.gtau[threadIdx.x] = 0ull;
     }
-    if (threadIdx.x == 0) {  // ready for the next launch on this stream
+    if (threadIdx.x == 0) {  // ready for the launch after next (this parity set)
         p.ticket[0] = 0u;
         p.ticket[1] = 0u;
+        if (p.stamps) p.stamps[blockIdx.x * 8 + 6] = globaltimer_ns();
     }
 }
 
@@ -640,11 +757,11 @@ scan_topk_kernel(const ScanParams p) {
 static inline size_t scan_smem_bytes(int variant, int nw, int QB, int qstride, int k, bool fullrank,
                                      uint32_t stages, uint32_t tile_bytes, uint32_t scratch_keys) {
     size_t ring = variant == B200_VARIANT_BULK ? (size_t)nw * stages * tile_bytes : 0;
-    size_t scratch = (size_t)scratch_keys * 8;
+    size_t scratch = (size_t)scratch_keys * 8 + B200_PREF_BYTES;
     size_t region0 = ring > scratch ? ring : scratch;
     region0 = (region0 + 127) & ~(size_t)127;
     size_t q = (size_t)QB * qstride * 4;
     size_t lists = fullrank ? 0 : (size_t)nw * QB * k * 8;
     size_t bars = variant == B200_VARIANT_BULK ? (size_t)nw * stages * (8 + 4) : 0;  // mbarriers + stage tiles
-    return region0 + q + lists + bars + 16;
+    return region0 + q + lists + bars + 16 + 4 * 16;  // + the per-query survivor counters
 }

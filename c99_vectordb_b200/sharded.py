@@ -157,7 +157,13 @@ class ShardedIndexFlat:
         # beats the scan from 2 queries on.  Every rank must hold rows (an empty shard launches no
         # kernel and nobody would flag for it).
         lo, hi = shard_range(self.ntotal_global, self.world, self.world - 1)
-        return self._fused and nq == 1 and k <= 256 and hi > lo
+        return self._fused and nq == 1 and k <= 256 and self.world * k <= 4096 and hi > lo
+
+    def check_exchange(self) -> None:
+        """Raise if a fused exchange timed out (a peer GPU never delivered: the affected search returned padding
+        only).  Call after synchronising the stream the searches ran on; search() does it for every call."""
+        if self._fused and _cabi.load().b200_index_exchange_status(self.local.index._h) != 0:
+            raise RuntimeError("fused exchange: a peer GPU did not deliver its results in time; the search returned no results")
 
     # ---- search -----------------------------------------------------------------------------
     def _buffers(self, nq: int, k: int):
@@ -221,6 +227,7 @@ class ShardedIndexFlat:
         hD.copy_(D, non_blocking=True)
         hI.copy_(I, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        self.check_exchange()
         return hD.numpy().copy(), hI.numpy().copy()
 
     # ---- pieces -----------------------------------------------------------------------------

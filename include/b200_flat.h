@@ -146,7 +146,16 @@ int b200_index_add_synthetic(b200_index* ix, int64_t n, uint64_t seed, int64_t f
 int b200_index_search(b200_index* ix, const float* q_host, int64_t nq, int64_t k, float* D_host,
                       int64_t* I_host);
 /* device-resident variant: q, D, I are device pointers; work is enqueued on `stream`
- * (a cudaStream_t; NULL = the handle's own stream) and NOT synchronised. */
+ * (a cudaStream_t; NULL = the handle's own stream).  Single queries (nq < option gemm_min_nq), masked
+ * scans and k > 256 are enqueued and NOT synchronised.  Batches on the tensor-core path block the host
+ * once per call: the certificates are read back to pick the (rare) queries that are recomputed.
+ * A handle owns one set of scratch buffers: calls are serialised by the caller on the host, and when
+ * consecutive calls name different streams the library orders the new stream behind the previous one
+ * (event record + wait), so streams passed here must stay alive while the handle may still use them.
+ * Back-to-back searches on one stream overlap through programmatic dependent launch (option scan_pdl,
+ * default on): the next launch ramps up while the previous one merges; with option queries_stable = 1
+ * (a promise that queries are never produced by the kernel immediately preceding the search on its
+ * stream) the whole scan overlaps. */
 int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev,
                           int64_t* I_dev, void* stream);
 /* filtered search (push memo's metadata filter down into the scan instead of
@@ -173,8 +182,11 @@ int b200_index_search_ids_allowed(b200_index* ix, const float* q_host, int64_t n
  *   b200_ipc_open    map a peer's handle into this process (enables peer access lazily)
  *   b200_index_set_exchange   peer_bufs[g] = rank g's buffer as mapped here (own buffer for g=rank);
  *                    every buffer holds 2 * world * b200_exchange_slot_bytes() bytes
- *   b200_index_search_exchange_dev   like search_dev for nq <= 8 per launch group and k <= 256, but
- *                    D/I receive the GLOBAL merged result; every rank must call it for every search */
+ *   b200_index_search_exchange_dev   like search_dev for nq <= 8 per launch group and k <= 256
+ *                    (world x nq x k <= 4096 entries), but D/I receive the GLOBAL merged result; every rank
+ *                    must call it for every search
+ *   b200_index_exchange_status       0 = every exchange so far completed; 1 = a peer did not deliver within
+ *                    ~2 s: that search returned padding only (ids -1).  Read after synchronising the stream. */
 int b200_ipc_alloc(void** out_dev, size_t bytes, char handle_out[64]);
 int b200_ipc_open(const char handle[64], void** out_dev);
 int b200_ipc_close(void* dev);
@@ -183,6 +195,12 @@ size_t b200_exchange_slot_bytes(void);
 int b200_index_set_exchange(b200_index* ix, int world, int rank, void* const* peer_bufs);
 int b200_index_search_exchange_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k,
                                    float* D_dev, int64_t* I_dev, void* stream);
+int b200_index_exchange_status(b200_index* ix);
+/* profiling aid: with option scan_phase_stamps = 1 every scan launch records per-CTA globaltimer stamps
+ * (ns): out[cta*8 + j], j = 0 kernel entry, 1 queries staged, 2 scan done (warp 0), 3 CTA reduction
+ * written, 4 last CTA starts the final merge, 5 final merge done, 6 kernel end (last CTA), 7 first tile
+ * landed (warp 0); 0 = not reached.  n_ctas receives the grid size of the last scan launch. */
+int b200_index_read_phase_stamps(b200_index* ix, unsigned long long* out_host, int64_t cap_words, int64_t* n_ctas);
 /* kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t b200_index_launch_count(b200_index* ix);
 /* block until the handle's stream is idle */

@@ -64,6 +64,16 @@ int oracle_max_threads(void) {
 #endif
 }
 
+/* Thread count of the OpenMP regions below.  bench.py sets it explicitly: under torchrun the environment carries
+ * OMP_NUM_THREADS=1, which would silently turn the "all host cores" baseline into a one-core one. */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ---- synthetic generator: integer-exact twin of csrc/common.cuh b200_synth_value ------------ */
 static inline uint32_t synth_bits(uint64_t seed, uint64_t ctr) {
     uint64_t z = ctr + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
@@ -387,8 +397,8 @@ void oracle_merge_topk(int metric, int G, int64_t nq, int64_t k, const float* Dp
             int best = -1;
             for (int g = 0; g < G; ++g) {
                 if (pos[g] >= k) continue;
-                int64_t ig = Ip[((int64_t)g * nq + q) * k + pos[g]];
-                if (ig < 0) continue; /* padding: this shard is exhausted */
+                float sg0 = Dp[((int64_t)g * nq + q) * k + pos[g]];
+                if (!score_valid(metric, sg0)) continue; /* padding (sentinel score): this shard is exhausted; negative ids are legal */
                 if (best < 0) {
                     best = g;
                     continue;

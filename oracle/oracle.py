@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
         L.oracle_merge_topk.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, fp, ip, fp, ip]
         L.oracle_merge_topk.restype = None
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_set_threads.argtypes = [C.c_int]
+        L.oracle_set_threads.restype = None
         _lib = L
     return _lib
 
@@ -98,6 +100,11 @@ def _pi(a):
 
 def max_threads() -> int:
     return int(lib().oracle_max_threads())
+
+
+def set_threads(n: int) -> None:
+    """Thread count of the oracle's OpenMP loops (overrides an inherited OMP_NUM_THREADS)."""
+    lib().oracle_set_threads(int(n))
 
 
 def synth_rows(n: int, d: int, seed: int, first_row: int = 0) -> np.ndarray:
