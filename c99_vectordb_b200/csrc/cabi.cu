@@ -24,10 +24,10 @@
 #include "rows.cuh"
 #include "scan_topk.cuh"
 
-// one (parity, sender) slot of the fused exchange: 16 spare bytes + up to 4096 entries of three self-validating
-// 8-byte words (id low | epoch, id high | epoch, score bits | epoch)
-#define XCHG_MAX_ENTRIES 4096
-#define XCHG_SLOT_BYTES ((size_t)16 + (size_t)XCHG_MAX_ENTRIES * 24)
+// one (parity, sender) slot of the fused exchange: 16 spare bytes + up to 8 queries x 256 results of three
+// self-validating 8-byte words (id low | epoch, id high | epoch, score bits | epoch)
+#define XCHG_SLOT_ENTRIES (8 * B200_FUSED_K_MAX)
+#define XCHG_SLOT_BYTES ((size_t)16 + (size_t)XCHG_SLOT_ENTRIES * 24)
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -69,15 +69,13 @@ struct b200_index {
     int ids_state = 0;  // 0 undecided, 1 explicit ids, 2 ids == row positions
     cudaStream_t stream = nullptr;
     int num_sms = 0;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0, smem_per_sm = 0;
     // scratch
     // per-launch control words and survivor lists of the scan kernel, double-buffered by launch parity so that
     // back-to-back launches may overlap (programmatic dependent launch)
-    uint64_t* partials = nullptr;   // [2][grid, QB, warps*k]
+    uint64_t* partials = nullptr;   // [2][grid, QB, k] per-CTA best keys
     size_t partials_cap = 0;        // keys per parity set
-    unsigned int* part_count = nullptr;  // [2][grid, QB]
-    size_t part_count_cap = 0;           // words per parity set
-    unsigned long long* ctl = nullptr;   // [2][16]: word 0 = {ticket, tile counter}, words 1..8 = thresholds per query
+    unsigned long long* ctl = nullptr;   // [2][16]: word 0 = {ticket, tile counter}
     uint64_t launch_seq = 0;
     unsigned long long* stamps = nullptr;  // [grid, 8] phase stamps of the last scan launch (option scan_phase_stamps)
     size_t stamps_cap = 0;
@@ -102,7 +100,7 @@ struct b200_index {
     int64_t opt_variant = B200_SCAN_AUTO, opt_warps = 16, opt_stages = 0, opt_tile_rows = 0,
             opt_ctas_per_sm = 0, opt_evict_first = 0, opt_fullrank_min_k = B200_FUSED_K_MAX + 1,
             opt_normalize_queries = 0, opt_staged_results = 1, opt_qb = 0, opt_dynamic = -1, opt_claim_chunk = 0, opt_fused_tail = -1,
-            opt_claim_min = 0, opt_pdl = 1, opt_queries_stable = 0, opt_phase_stamps = 0, opt_fuse_query_norm = 1;
+            opt_claim_min = 0, opt_claim_first = 0, opt_pdl = 1, opt_queries_stable = 0, opt_phase_stamps = 0, opt_fuse_query_norm = 1;
     bool cur_norm_q = false;  // the scan launches of the search in flight normalise their queries themselves
     int64_t opt_gemm_min_rows = 4096, opt_gemm_min_nq = 2, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2;
     // read-only statistics of the last batched (K3) search
@@ -239,6 +237,7 @@ extern "C" int b200_index_create(b200_index** out, int d, int metric, int store,
     ix->lpr = pick_lpr(ix->pitch / 16);  // part of the index's numerics: fixed at creation
     ix->num_sms = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
+    ix->smem_per_sm = prop.sharedMemPerMultiprocessor;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc((void**)&ix->ctl, 2 * 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(ix->ctl, 0, 2 * 16 * sizeof(unsigned long long));
@@ -258,7 +257,6 @@ extern "C" int b200_index_destroy(b200_index* ix) {
     cudaFree(ix->rows);
     cudaFree(ix->ids);
     cudaFree(ix->partials);
-    cudaFree(ix->part_count);
     cudaFree(ix->ctl);
     cudaFree(ix->stamps);
     if (ix->order_ev) cudaEventDestroy(ix->order_ev);
@@ -367,6 +365,7 @@ static const OptName kOpts[] = {
     {"scan_claim_chunk", &b200_index::opt_claim_chunk},
     {"scan_fused_tail", &b200_index::opt_fused_tail},
     {"scan_claim_min", &b200_index::opt_claim_min},
+    {"scan_claim_first", &b200_index::opt_claim_first},
     {"scan_pdl", &b200_index::opt_pdl},
     {"queries_stable", &b200_index::opt_queries_stable},
     {"scan_phase_stamps", &b200_index::opt_phase_stamps},
@@ -1071,7 +1070,7 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
     pl.qb = qb;
     const int qstride = (ix->d_pad + 7) / 8 * 8;
     const int kk = fullrank ? 1 : k;
-    const size_t budget = ix->smem_optin - 1024;
+    size_t budget = ix->smem_optin - 1024;
     const uint32_t step_rows = SCAN_RB * (32u / (uint32_t)ix->lpr);  // rows one warp step covers
     int variant = (int)ix->opt_variant;
     // AUTO (measured over d = 64..2048, fp32 and bf16: profiles/README.md, r1_sweep11_*, r1_sweep13_*):
@@ -1084,7 +1083,13 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
     const bool auto_variant = variant == B200_SCAN_AUTO;
     if (auto_variant) variant = (ix->pitch >= 512 || ix->lpr == 8) ? B200_VARIANT_BULK : B200_VARIANT_LDG;
     if (variant == B200_VARIANT_BULK) {
-        int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), (qb >= 4 ? 256 : B200_SCAN_THREADS_BULK) / 32);
+        // CTAs per SM (option scan_ctas_per_sm, default 1): c co-resident CTAs share the SM's shared memory and warp
+        // slots, so that at a launch boundary (programmatic dependent launch) an SM is handed over one CTA at a time
+        // instead of idling between the old CTA's exit and the new CTA's first tile.
+        const int ctas = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_ctas_per_sm, 1), 4);
+        if (ctas > 1) budget = std::min(budget, ix->smem_per_sm / ctas - 1024 - 256);
+        int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), (qb >= 4 ? 256 : B200_SCAN_THREADS_BULK) / 32 / ctas);
+        nw = std::max(nw, 1);
         const int nw_min = auto_variant ? 3 : 1;
         bool ok = false;
         // Every warp owns `stages` tiles of tile_rows rows.  Prefer ~12 KB tiles, but shrink the tile
@@ -1101,7 +1106,7 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
                 uint32_t tr = m * step_rows;
                 uint64_t tile_bytes = (uint64_t)tr * ix->pitch;
                 if (tile_bytes > (1u << 19)) continue;  // mbarrier tx-count headroom
-                const uint32_t scratch = B200_FINAL_BUF_KEYS;
+                const uint32_t scratch = std::max<uint32_t>(B200_FINAL_BUF_KEYS, next_pow2((uint32_t)(nw * kk)));
                 size_t fixed = scan_smem_bytes(B200_VARIANT_BULK, nw, qb, qstride, kk, fullrank, 0, 0, scratch);
                 // ring replaces the scratch region when larger
                 size_t fixed_wo_scratch = fixed - (((size_t)scratch * 8 + B200_PREF_BYTES + 127) & ~(size_t)127);
@@ -1119,7 +1124,7 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
                 pl.tile_bytes = (uint32_t)tile_bytes;
                 pl.scratch_keys = scratch;
                 pl.smem = smem;
-                pl.grid = ix->num_sms;  // one persistent CTA per SM
+                pl.grid = ix->num_sms * ctas;  // persistent CTAs
                 ok = true;
             }
         }
@@ -1129,7 +1134,7 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
         int nw = (int)std::min<int64_t>(std::max<int64_t>(ix->opt_warps, 1), B200_SCAN_THREADS_LDG / 32);
         for (;; nw >>= 1) {
             if (nw < 1) return fail("k=%d does not fit the fused top-k shared-memory budget", k);
-            const uint32_t scratch = B200_FINAL_BUF_KEYS;
+            const uint32_t scratch = std::max<uint32_t>(B200_FINAL_BUF_KEYS, next_pow2((uint32_t)(nw * kk)));
             size_t smem = scan_smem_bytes(B200_VARIANT_LDG, nw, qb, qstride, kk, fullrank, 0, 0, scratch);
             if (smem > budget) continue;
             pl.variant = B200_VARIANT_LDG;
@@ -1178,7 +1183,6 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     p.normalize_q = ix->cur_norm_q ? 1 : 0;
     const int set = (int)(ix->launch_seq++ & 1);  // control words and survivor lists of this launch's parity
     p.ticket = reinterpret_cast<unsigned int*>(ix->ctl + (size_t)set * 16);
-    p.gtau = ix->ctl + (size_t)set * 16 + 1;
     p.dynamic = ix->opt_dynamic < 0 ? (pl.variant == B200_VARIANT_BULK ? 1 : 0) : (ix->opt_dynamic ? 1 : 0);
     {
         // One atomic claim hands out a run of tiles.  The run bounds the tail (a warp finishes at
@@ -1191,6 +1195,10 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
         if (ix->opt_claim_chunk > 0) p.claim_chunk = (uint32_t)ix->opt_claim_chunk;
         p.claim_min = ix->opt_claim_min > 0 ? (uint32_t)ix->opt_claim_min : 2u;
         if (p.claim_min > p.claim_chunk) p.claim_min = p.claim_chunk;
+        // the first run of every warp is static; small databases spread their tiles over all warps
+        const uint64_t warps = (uint64_t)pl.grid * pl.nw;
+        p.claim_first = (uint32_t)std::min<uint64_t>(p.claim_chunk, std::max<uint64_t>(1, tiles / warps));
+        if (ix->opt_claim_first > 0) p.claim_first = (uint32_t)std::min<uint64_t>((uint64_t)ix->opt_claim_first, std::max<uint64_t>(1, tiles / warps));
     }
     p.fused_tail = (nqb == 1 || score_keys) ? 1 : 0;
     if (ix->opt_fused_tail >= 0) p.fused_tail = ix->opt_fused_tail ? 1 : 0;
@@ -1206,8 +1214,6 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     p.row_mask = ix->cur_mask;
     p.scratch_keys = pl.scratch_keys;
     if (ix->xchg_active && !score_keys) {
-        if ((int64_t)ix->xchg_world * nqb * k > XCHG_MAX_ENTRIES)
-            return fail("fused exchange: world x queries x k = %lld entries exceed %d", (long long)ix->xchg_world * nqb * k, XCHG_MAX_ENTRIES);
         p.xchg_peers = ix->xchg_peers_dev;
         p.xchg_world = ix->xchg_world;
         p.xchg_rank = ix->xchg_rank;
@@ -1216,29 +1222,18 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
         p.xchg_status = ix->xchg_status;
         p.fused_tail = 1;  // the exchange lives in the last CTA's tail
     }
-    if (pl.grid > 1023) return fail("scan grid of %d CTAs exceeds the final merge's prefix table", pl.grid);
+    if (pl.grid > 1024) return fail("scan grid of %d CTAs exceeds the final merge's selector table", pl.grid);
     if (!score_keys) {
-        p.part_cap = (uint32_t)(pl.nw * k);
-        const size_t need = (size_t)pl.grid * pl.qb * p.part_cap, need_c = (size_t)pl.grid * pl.qb;
-        if (ix->partials_cap < need || ix->part_count_cap < need_c) {
-            CK(cudaStreamSynchronize(st));  // launches in flight still use the old buffers
-            if (ix->partials_cap < need) {
-                if (ix->partials) CK(cudaFree(ix->partials));
-                ix->partials = nullptr;
-                ix->partials_cap = 0;
-                CK(cudaMalloc((void**)&ix->partials, 2 * need * sizeof(uint64_t)));
-                ix->partials_cap = need;
-            }
-            if (ix->part_count_cap < need_c) {
-                if (ix->part_count) CK(cudaFree(ix->part_count));
-                ix->part_count = nullptr;
-                ix->part_count_cap = 0;
-                CK(cudaMalloc((void**)&ix->part_count, 2 * need_c * sizeof(unsigned int)));
-                ix->part_count_cap = need_c;
-            }
+        const size_t need = (size_t)pl.grid * pl.qb * k;
+        if (ix->partials_cap < need) {
+            CK(cudaStreamSynchronize(st));  // launches in flight still use the old buffer
+            if (ix->partials) CK(cudaFree(ix->partials));
+            ix->partials = nullptr;
+            ix->partials_cap = 0;
+            CK(cudaMalloc((void**)&ix->partials, 2 * need * sizeof(uint64_t)));
+            ix->partials_cap = need;
         }
         p.partials = ix->partials + (size_t)set * ix->partials_cap;
-        p.part_count = ix->part_count + (size_t)set * ix->part_count_cap;
     }
     if (ix->opt_phase_stamps) {
         const size_t need = (size_t)pl.grid * 8;
@@ -2001,8 +1996,6 @@ extern "C" int b200_index_search_exchange_dev(b200_index* ix, const float* q_dev
     if (k > B200_FUSED_K_MAX || k >= ix->opt_fullrank_min_k) return fail("fused exchange needs k <= %d", B200_FUSED_K_MAX);
     if (ix->ntotal == 0) return fail("fused exchange needs at least one row on every rank");
     if (*ix->xchg_status_host) return fail("fused exchange: a peer GPU did not deliver its results in time during an earlier search");
-    if ((int64_t)ix->xchg_world * std::min<int64_t>(nq, 8) * k > XCHG_MAX_ENTRIES)
-        return fail("fused exchange: world x queries x k exceeds %d entries", XCHG_MAX_ENTRIES);
     ix->xchg_active = true;
     int rc = b200_index_search_dev(ix, q_dev, nq, k, D_dev, I_dev, stream);
     ix->xchg_active = false;

@@ -45,7 +45,7 @@
 #define B200_SCAN_THREADS_LDG 256   // direct-load variant: 4 CTAs of 8 warps per SM (<= 64 registers)
 #define B200_FUSED_K_MAX 256
 #define B200_FINAL_BUF_KEYS 2048
-#define B200_PREF_BYTES 4096u       // prefix sums of the per-CTA survivor counts: grids of up to 1023 CTAs
+#define B200_PREF_BYTES 8192u       // one 64-bit selector key per CTA in the final merge: grids of up to 1024 CTAs
 
 struct ScanParams {
     const uint8_t* rows;      // row storage
@@ -57,14 +57,13 @@ struct ScanParams {
     int qstride;              // padded floats per query in shared memory (multiple of 8)
     int nqb;                  // queries in this launch (<= QB)
     int k;                    // results per query (top-k mode)
-    uint64_t* partials;       // [grid, QB, part_cap] per-CTA surviving keys (unsorted)
-    unsigned int* part_count; // [grid, QB] number of surviving keys per CTA and query
-    uint32_t part_cap;        // warps * k
-    unsigned long long* gtau; // [QB] global threshold of this launch: max over CTAs of their best k-th key (0 = none yet)
+    uint64_t* partials;       // [grid, QB, k] per-CTA best keys, sorted best-first, zero padded
     unsigned int* ticket;     // [0] CTA-done ticket, [1] tile counter; zero before launch, reset by the last CTA
     int dynamic;              // 1: tiles claimed in order from the global counter; 0: static striding
     uint32_t claim_chunk;     // dynamic: most consecutive tiles taken per atomic claim (>= 1)
     uint32_t claim_min;       // dynamic: fewest (the run shrinks with the tiles that remain)
+    uint32_t claim_first;     // dynamic: every warp's first run is static (warp w: tiles [w, w+1) * claim_first), so a
+                              // launch does not start with one atomic per warp on a single address (~2.5 ns each)
     int pdl;                  // 0: plain launch; 1: launched with programmatic stream serialisation, queries may come
                               // from the preceding kernel (wait before reading them); 2: queries are stable (wait after the scan)
     int normalize_q;          // 1: L2-normalise the queries while staging them (K1 arithmetic, memo_cli.py:131-135)
@@ -87,7 +86,7 @@ struct ScanParams {
     uint32_t xchg_epoch;      // strictly increasing per launch
     uint32_t xchg_slot_bytes; // bytes of one (parity, sender) slot
     int* xchg_status;         // set to 1 if a peer never showed up
-    uint32_t scratch_keys;    // B200_FINAL_BUF_KEYS (power of two >= 2k)
+    uint32_t scratch_keys;    // power of two >= max(warps*k, B200_FINAL_BUF_KEYS)
 };
 
 // ---- small device pieces ---------------------------------------------------------------------
@@ -167,66 +166,97 @@ __device__ __forceinline__ void cta_bitonic_sort_desc(uint64_t* a, uint32_t m) {
     __syncthreads();
 }
 
-// Final merge of query qi by the whole CTA: every CTA left part_count[cta] surviving keys (unsorted, each >= that
-// CTA's own threshold); keys below the launch's global threshold gtau cannot be among the best k (some warp holds k
-// keys >= gtau), so typically only k + a few dozen keys pass the filter.  They are collected in `scratch` (B keys) in
-// ONE pass over all CTAs — a window of the flat survivor sequence never holds more keys than the buffer has room for —
-// sorted, and the first k are translated row -> record id (K5) and written.  Adversarial inputs (thousands of keys
-// above the threshold) take further windows, re-sorting and tightening the threshold between them.
-// s_pref: nctas + 1 words of shared memory (exclusive prefix sums of the counts).
+// Rank-by-counting selection in shared memory: keys[0..n) are distinct 64-bit keys (0 = empty slot).  Every non-empty
+// key counts the keys above it and, if fewer than k are, writes itself to out[rank]: out[0..k) ends up sorted
+// best-first without a sort network or atomics; slots past the number of non-empty keys are zeroed.  n^2 / threads
+// comparisons of broadcast shared-memory reads — used for n <= B200_COUNT_SELECT_MAX.  Whole CTA; `counter`: one
+// shared word.  out may be global or shared memory (not aliasing keys).
+#define B200_COUNT_SELECT_MAX 1024
+__device__ __forceinline__ void cta_count_select(const uint64_t* keys, uint32_t n, int k, uint64_t* out, unsigned int* counter) {
+    if (threadIdx.x == 0) *counter = 0u;
+    __syncthreads();
+    unsigned int mine = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t key = keys[i];
+        if (key == 0ull) continue;
+        ++mine;
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n; ++j) rank += keys[j] > key ? 1u : 0u;
+        if (rank < (uint32_t)k) out[rank] = key;
+    }
+    if (mine) atomicAdd(counter, mine);
+    __syncthreads();
+    for (uint32_t r = *counter + threadIdx.x; r < (uint32_t)k; r += blockDim.x) out[r] = 0ull;
+    __syncthreads();  // the counter may be reused at once
+}
+
+// Final merge of query qi by the whole CTA.  Every CTA left its best k keys sorted best-first (zero padded).
+//  1. Threshold: with j = ceil(k / min(k, nctas)) and m = ceil(k / j), T = the m-th largest of the CTAs' j-th keys.
+//     m lists hold >= j keys >= T each, i.e. >= k keys in total, so the global k-th best cannot be below T.  For
+//     k <= nctas this is the k-th largest CTA maximum — tight: typically only k..2k keys are >= T.
+//  2. One pass over all nctas*k keys (the first batch is already in flight while T is computed) keeps the keys
+//     >= T in `scratch` (B keys); a window of the key sequence never holds more keys than the buffer has room for, and
+//     adversarial inputs (thousands of keys >= T) take further windows, re-sorting and tightening T between them.
+//  3. The survivors are sorted, the first k translated row -> record id (K5) and written.
+// s_sel: nctas 64-bit words of shared memory.
 template <int METRIC, int QB>
 __device__ __forceinline__ void final_merge_one(const ScanParams& p, int qi, uint32_t nctas, uint64_t* scratch,
-                                                unsigned int* sctr, uint32_t* s_pref) {
+                                                unsigned int* sctr, uint64_t* s_sel) {
     const int k = p.k;
     const uint32_t B = p.scratch_keys;
+    const uint32_t total = nctas * (uint32_t)k;
+    const uint32_t kk = (uint32_t)k < nctas ? (uint32_t)k : nctas;
+    const uint32_t j = ((uint32_t)k + kk - 1) / kk, m = ((uint32_t)k + j - 1) / j;
+    auto key_at = [&](uint32_t i) {  // flat index over (cta, position)
+        const uint32_t c = i / (uint32_t)k, r = i - c * (uint32_t)k;
+        return __ldcg(p.partials + ((size_t)c * QB + qi) * k + r);
+    };
     __syncthreads();
-    for (uint32_t c = threadIdx.x; c < nctas; c += blockDim.x) s_pref[c + 1] = __ldcg(p.part_count + (size_t)c * QB + qi);
-    if (threadIdx.x == 0) {
-        s_pref[0] = 0u;
-        *sctr = 0u;
-    }
-    const unsigned long long g = __ldcg(p.gtau + qi);
-    uint64_t thr = g ? (uint64_t)g - 1ull : 0ull;  // keep key > thr  <=>  key >= gtau (any non-empty key when no list was full)
-    __syncthreads();
-    if (threadIdx.x < 32) {  // inclusive scan of the counts by one warp
-        uint32_t carry = 0;
-        for (uint32_t base = 0; base < nctas; base += 32) {
-            const uint32_t i = base + threadIdx.x;
-            uint32_t v = i < nctas ? s_pref[i + 1] : 0u;
+    for (uint32_t c = threadIdx.x; c < nctas; c += blockDim.x) s_sel[c] = __ldcg(p.partials + ((size_t)c * QB + qi) * k + (j - 1));
+    constexpr int U = 8;  // keys in flight per thread
+    uint64_t key[U];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t u = __shfl_up_sync(B200_FULL_MASK, v, o);
-                if ((int)threadIdx.x >= o) v += u;
-            }
-            if (i < nctas) s_pref[i + 1] = v + carry;
-            carry += __shfl_sync(B200_FULL_MASK, v, 31);
+    for (int u = 0; u < U; ++u) {
+        const uint32_t i = threadIdx.x + (uint32_t)u * blockDim.x;
+        key[u] = i < total ? key_at(i) : 0ull;
+    }
+    if (threadIdx.x == 0) sctr[0] = 0u;  // sctr[1], sctr[2]: high / low word of T
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < nctas; c += blockDim.x) {
+        const uint64_t v = s_sel[c];
+        uint32_t rank = 0;  // entries ahead of this one: larger value, or equal value (zeros) at a smaller index
+        for (uint32_t c2 = 0; c2 < nctas; ++c2) {
+            const uint64_t w = s_sel[c2];
+            rank += (w > v || (w == v && c2 < c)) ? 1u : 0u;
+        }
+        if (rank == m - 1) {
+            sctr[1] = (uint32_t)(v >> 32);
+            sctr[2] = (uint32_t)v;
         }
     }
     __syncthreads();
-    const uint32_t total = s_pref[nctas];
+    const uint64_t T = ((uint64_t)sctr[1] << 32) | sctr[2];
+    uint64_t thr = T ? T - 1ull : 0ull;  // keep key > thr  <=>  key >= T (any non-empty key when fewer than m lists reach j keys)
     uint32_t pos = 0, filled = 0;
+    bool preloaded = true;  // key[] holds items threadIdx.x + u * blockDim.x
     do {
         const uint32_t room = B - filled;
         const uint32_t end = total - pos < room ? total : pos + room;
-        constexpr int U = 4;  // loads in flight per thread
         for (uint32_t i0 = pos + threadIdx.x; i0 < end; i0 += blockDim.x * U) {
-            uint64_t key[U];
+            const bool have = preloaded && i0 == threadIdx.x;
+            preloaded = false;
+            if (!have) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t i = i0 + (uint32_t)u * blockDim.x;
-                key[u] = 0ull;
-                if (i < end) {
-                    uint32_t lo = 0, hi = nctas;  // the CTA whose range [pref[c], pref[c+1]) holds item i
-                    while (hi - lo > 1) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (s_pref[mid] <= i) lo = mid; else hi = mid;
-                    }
-                    key[u] = __ldcg(p.partials + ((size_t)lo * QB + qi) * p.part_cap + (i - s_pref[lo]));
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+                    key[u] = i < total ? key_at(i) : 0ull;
                 }
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (key[u] > thr) scratch[atomicAdd(sctr, 1u)] = key[u];
+            for (int u = 0; u < U; ++u) {
+                const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+                if (i < end && key[u] > thr) scratch[atomicAdd(sctr, 1u)] = key[u];
+            }
         }
         pos = end;
         __syncthreads();
@@ -287,15 +317,24 @@ __device__ __forceinline__ void final_merge_one(const ScanParams& p, int qi, uin
 // Kernels on DIFFERENT GPUs wait on one another here — never two kernels of one GPU.  A peer that does not deliver
 // within ~2 s marks the launch failed: every result is padding (-1) and *xchg_status is set.
 // Padding entries are recognised by their sentinel score, not by a negative id (negative record ids are legal).
-// s_h: world * nqb * k words of shared memory.
+// s_h: s_h_cap words of shared memory for the entries' score keys; exchanges with more entries than that (large
+// k x queries x world) look the keys up in the exchange buffer itself.
 template <int METRIC>
-__device__ __forceinline__ void exchange_and_merge(const ScanParams& p, uint32_t* s_h) {
+__device__ __forceinline__ void exchange_and_merge(const ScanParams& p, uint32_t* s_h, uint32_t s_h_cap) {
     const int k = p.k, G = p.xchg_world;
     const uint8_t* own = p.xchg_peers[p.xchg_rank] + (size_t)(p.xchg_epoch & 1u) * G * p.xchg_slot_bytes;
     const int total = G * p.nqb * k;
     auto words_of = [&](int t) {  // entry t enumerates (q, g, j)
         const int q = t / (G * k), r = t - q * (G * k), g = r / k, j = r - g * k;
         return reinterpret_cast<const uint64_t*>(own + (size_t)g * p.xchg_slot_bytes + 16 + ((size_t)q * k + j) * 24);
+    };
+    const bool in_smem = (uint32_t)total <= s_h_cap;
+    auto key_of = [&](int t) -> uint32_t {  // score key of entry t (0 = padding), once every entry has arrived
+        if (in_smem) return s_h[t];
+        uint64_t w2;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w2) : "l"(words_of(t) + 2) : "memory");
+        const float sc = __uint_as_float((uint32_t)w2);
+        return b200_score_valid<METRIC>(sc) ? b200_key_hi<METRIC>(sc) : 0u;
     };
     int64_t id0 = -1;
     float sc0 = 0.0f;
@@ -315,7 +354,7 @@ __device__ __forceinline__ void exchange_and_merge(const ScanParams& p, uint32_t
             }
         }
         const float sc = __uint_as_float((uint32_t)w2);
-        s_h[t] = (timed_out || !b200_score_valid<METRIC>(sc)) ? 0u : b200_key_hi<METRIC>(sc);
+        if (in_smem) s_h[t] = (timed_out || !b200_score_valid<METRIC>(sc)) ? 0u : b200_key_hi<METRIC>(sc);
         if (t == (int)threadIdx.x) {
             id0 = (int64_t)((w0 & 0xffffffffull) | (w1 << 32));
             sc0 = sc;
@@ -343,15 +382,15 @@ __device__ __forceinline__ void exchange_and_merge(const ScanParams& p, uint32_t
             id = (int64_t)((w0 & 0xffffffffull) | (w1 << 32));
             sc = __uint_as_float((uint32_t)w2);
         }
-        const uint32_t h = s_h[t];
+        const uint32_t h = key_of(t);
         int rank = j;
         for (int g2 = 0; g2 < G; ++g2) {
             if (g2 == g) continue;
-            const uint32_t* H2 = s_h + ((size_t)q * G + g2) * k;
+            const int base2 = (q * G + g2) * k;
             int lo = 0, hi = k;  // entries of list g2 that precede this candidate
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                const uint32_t hm = H2[mid];
+                const uint32_t hm = key_of(base2 + mid);
                 const bool before = (g2 < g) ? (hm >= h) : (hm > h);
                 if (before) lo = mid + 1; else hi = mid;
             }
@@ -371,9 +410,8 @@ __global__ void __launch_bounds__(256) final_merge_kernel(const ScanParams p, ui
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* scratch = reinterpret_cast<uint64_t*>(smem);
     unsigned int* sctr = reinterpret_cast<unsigned int*>(smem + (size_t)p.scratch_keys * 8);
-    uint32_t* s_pref = reinterpret_cast<uint32_t*>(sctr + 4);
-    final_merge_one<METRIC, QB>(p, blockIdx.x, nctas, scratch, sctr, s_pref);
-    if (threadIdx.x == 0) p.gtau[blockIdx.x] = 0ull;  // ready for the launch after next (same parity set)
+    uint64_t* s_sel = reinterpret_cast<uint64_t*>(sctr + 4);
+    final_merge_one<METRIC, QB>(p, blockIdx.x, nctas, scratch, sctr, s_sel);
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
@@ -398,12 +436,12 @@ scan_topk_kernel(const ScanParams p) {
     // ---- shared memory carve-up (host computes the same sizes: scan_smem_bytes) ----
     // [ring: nw*stages*tile_bytes | scratch (aliases ring start)] [queries] [lists] [mbarriers] [ctr] [stage tiles]
     uint32_t ring_bytes = (VARIANT == B200_VARIANT_BULK) ? nw * p.stages * p.tile_bytes : 0u;
-    uint32_t scratch_bytes = p.scratch_keys * 8u + B200_PREF_BYTES;  // final-merge buffer + per-CTA count prefix sums
+    uint32_t scratch_bytes = p.scratch_keys * 8u + B200_PREF_BYTES;  // final-merge buffer + one selector key per CTA
     uint32_t region0 = ring_bytes > scratch_bytes ? ring_bytes : scratch_bytes;
     region0 = (region0 + 127u) & ~127u;
     uint8_t* ring = smem;
     uint64_t* scratch = reinterpret_cast<uint64_t*>(smem);
-    uint32_t* s_pref = reinterpret_cast<uint32_t*>(smem + p.scratch_keys * 8u);
+    uint64_t* s_sel = reinterpret_cast<uint64_t*>(smem + p.scratch_keys * 8u);
     float* qs = reinterpret_cast<float*>(smem + region0);
     uint32_t q_bytes = (uint32_t)QB * p.qstride * 4u;
     uint64_t* lists = reinterpret_cast<uint64_t*>(smem + region0 + q_bytes);
@@ -427,7 +465,9 @@ scan_topk_kernel(const ScanParams p) {
     // and DRAM sees one advancing front.  static: warp gw takes tiles gw, gw+GW, ...
     uint32_t static_next = blockIdx.x * nw + warp;
     const uint32_t static_step = gridDim.x * nw;
-    uint32_t chunk_next = 0, chunk_end = 0;  // lane 0: the claimed run of consecutive tiles
+    uint32_t chunk_next = (blockIdx.x * nw + warp) * p.claim_first;  // lane 0: the claimed run of consecutive tiles
+    uint32_t chunk_end = chunk_next + p.claim_first;
+    const uint32_t claim_base = gridDim.x * nw * p.claim_first;       // the counter hands out tiles from here on
     const uint32_t guide_div = 2u * gridDim.x * (uint32_t)nw;
     auto claim = [&]() -> uint32_t {  // called by lane 0 only
         if (p.dynamic) {
@@ -439,7 +479,7 @@ scan_topk_kernel(const ScanParams p) {
                 const uint32_t left = chunk_end < tiles_total ? tiles_total - chunk_end : 0u;
                 uint32_t run = left / guide_div;
                 run = run < p.claim_min ? p.claim_min : (run > p.claim_chunk ? p.claim_chunk : run);
-                chunk_next = atomicAdd(p.ticket + 1, run);
+                chunk_next = claim_base + atomicAdd(p.ticket + 1, run);
                 chunk_end = chunk_next + run;
             }
             return chunk_next++;
@@ -695,37 +735,40 @@ scan_topk_kernel(const ScanParams p) {
     }
 
     if (p.stamps && threadIdx.x == 0) p.stamps[blockIdx.x * 8 + 2] = globaltimer_ns();
-    // ---- CTA reduction: keep the keys that can still be among the best k, unsorted ----
-    // tau of a warp is its k-th best key once its list is full (0 before): that warp alone proves k candidates
-    // >= tau, so nothing below the best warp threshold of this CTA can matter.
-    unsigned long long* s_tau = reinterpret_cast<unsigned long long*>(scratch);  // [nw, QB] (the ring has been consumed)
+    // ---- CTA reduction: the warps' lists -> this CTA's best k per query, sorted best-first ----
     __syncthreads();  // all warps done; every issued bulk copy has been consumed
     if (p.pdl == 2) {  // stable queries: this launch only has to be ordered behind the previous one from here on
         griddep_wait();
         griddep_launch_dependents();
     }
     if (!fullrank) {
-        if (lane == 0)
-#pragma unroll
-            for (int qi = 0; qi < QB; ++qi) s_tau[warp * QB + qi] = tau[qi];
-        if (threadIdx.x < QB) sctr[threadIdx.x] = 0u;
-        __syncthreads();
+        const uint32_t nkeys = (uint32_t)(nw * k);
         for (int qi = 0; qi < p.nqb; ++qi) {
-            unsigned long long t = 0ull;
-            for (int w = 0; w < nw; ++w) {
-                const unsigned long long v = s_tau[w * QB + qi];
-                t = v > t ? v : t;
+            uint64_t* out = p.partials + ((size_t)blockIdx.x * QB + qi) * k;
+            if (nkeys <= B200_COUNT_SELECT_MAX && (QB == 1 || nw == 1)) {
+                // the warps' lists of one query are contiguous: rank every key by counting (no sort, no atomics)
+                cta_count_select(lists + (size_t)qi * k, nkeys, k, out, sctr);
+            } else {
+                uint32_t mm = 2;
+                while (mm < nkeys) mm <<= 1;
+                for (uint32_t i = threadIdx.x; i < mm; i += blockDim.x) {
+                    uint64_t v = 0ull;
+                    if (i < nkeys) {
+                        uint32_t w = i / k, jj = i - w * k;
+                        v = lists[((size_t)w * QB + qi) * k + jj];
+                    }
+                    scratch[i] = v;
+                }
+                if (mm <= B200_COUNT_SELECT_MAX) {
+                    __syncthreads();
+                    cta_count_select(scratch, nkeys, k, out, sctr);
+                } else {
+                    cta_bitonic_sort_desc(scratch, mm);
+                    for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = scratch[i];
+                }
+                __syncthreads();
             }
-            uint64_t* out = p.partials + ((size_t)blockIdx.x * QB + qi) * p.part_cap;
-            for (int i = threadIdx.x; i < nw * k; i += blockDim.x) {
-                const int w = i / k, j = i - w * k;
-                const uint64_t key = lists[((size_t)w * QB + qi) * k + j];
-                if (key != 0ull && key >= t) out[atomicAdd(sctr + qi, 1u)] = key;
-            }
-            if (threadIdx.x == 0 && t) atomicMax(p.gtau + qi, t);
         }
-        __syncthreads();
-        if ((int)threadIdx.x < p.nqb) p.part_count[(size_t)blockIdx.x * QB + threadIdx.x] = sctr[threadIdx.x];
     }
     if (p.stamps && threadIdx.x == 0) p.stamps[blockIdx.x * 8 + 3] = globaltimer_ns();
 
@@ -741,10 +784,9 @@ scan_topk_kernel(const ScanParams p) {
     __threadfence();
     if (p.stamps && threadIdx.x == 0) p.stamps[blockIdx.x * 8 + 4] = globaltimer_ns();
     if (!fullrank && p.fused_tail) {
-        for (int qi = 0; qi < p.nqb; ++qi) final_merge_one<METRIC, QB>(p, qi, gridDim.x, scratch, sctr + QB, s_pref);
+        for (int qi = 0; qi < p.nqb; ++qi) final_merge_one<METRIC, QB>(p, qi, gridDim.x, scratch, sctr, s_sel);
         if (p.stamps && threadIdx.x == 0) p.stamps[blockIdx.x * 8 + 5] = globaltimer_ns();
-        if (p.xchg_peers) exchange_and_merge<METRIC>(p, reinterpret_cast<uint32_t*>(scratch));
-        if ((int)threadIdx.x < p.nqb) p.gtau[threadIdx.x] = 0ull;
+        if (p.xchg_peers) exchange_and_merge<METRIC>(p, reinterpret_cast<uint32_t*>(scratch), p.scratch_keys * 2u);
     }
     if (threadIdx.x == 0) {  // ready for the launch after next (this parity set)
         p.ticket[0] = 0u;

@@ -157,7 +157,7 @@ class ShardedIndexFlat:
         # beats the scan from 2 queries on.  Every rank must hold rows (an empty shard launches no
         # kernel and nobody would flag for it).
         lo, hi = shard_range(self.ntotal_global, self.world, self.world - 1)
-        return self._fused and nq == 1 and k <= 256 and self.world * k <= 4096 and hi > lo
+        return self._fused and nq == 1 and k <= 256 and hi > lo
 
     def check_exchange(self) -> None:
         """Raise if a fused exchange timed out (a peer GPU never delivered: the affected search returned padding

@@ -182,9 +182,8 @@ int b200_index_search_ids_allowed(b200_index* ix, const float* q_host, int64_t n
  *   b200_ipc_open    map a peer's handle into this process (enables peer access lazily)
  *   b200_index_set_exchange   peer_bufs[g] = rank g's buffer as mapped here (own buffer for g=rank);
  *                    every buffer holds 2 * world * b200_exchange_slot_bytes() bytes
- *   b200_index_search_exchange_dev   like search_dev for nq <= 8 per launch group and k <= 256
- *                    (world x nq x k <= 4096 entries), but D/I receive the GLOBAL merged result; every rank
- *                    must call it for every search
+ *   b200_index_search_exchange_dev   like search_dev for nq <= 8 per launch group and k <= 256, but D/I
+ *                    receive the GLOBAL merged result; every rank must call it for every search
  *   b200_index_exchange_status       0 = every exchange so far completed; 1 = a peer did not deliver within
  *                    ~2 s: that search returned padding only (ids -1).  Read after synchronising the stream. */
 int b200_ipc_alloc(void** out_dev, size_t bytes, char handle_out[64]);

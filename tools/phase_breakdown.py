@@ -49,6 +49,7 @@ def main():
         idx = m.IndexFlat(a.d, 0 if a.metric == "ip" else 1, store=a.store)
         idx.add_synthetic(n, 1234)
         idx.set_option("scan_phase_stamps", 1)
+        idx.set_option("scan_pdl", 0)  # anatomy of one launch alone (with PDL the kernel would wait for the stamp memset inside its prologue)
         q = torch.empty((a.reps + 3, 1, a.d), dtype=torch.float32, device=dev)
         for s in range(a.reps + 3):
             _cabi.check(L.b200_synth_rows_dev(q[s].data_ptr(), 1, a.d, 5678 + s, 0, 0, C.c_void_p(1)))
