@@ -130,31 +130,76 @@ def ncu_traffic(workload: str):
 
 
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  NVML in a
+    background thread every ~4 ms (an nvidia-smi subprocess needs longer to start than an 8-GPU timed region lasts);
+    the nvidia-smi query of the recipe is the fallback when the NVML binding is missing."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.samples = []  # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self.thread = None
         self.proc = None
+        self.tmp = None
+        self._stop = False
+
+    def _loop(self, nv, h):
+        while not self._stop:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
         try:
+            import threading
+
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [int(x) for x in vis.split(",") if x.strip().isdigit()]
+            phys = ids[self.gpu] if self.gpu < len(ids) else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+            self.thread = threading.Thread(target=self._loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                 stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            nv = self.nv
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+            names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+            reasons = sorted({n for _, bits in self.samples for n, bit in names if bits & bit})
+            return {"sm_mhz": statistics.median(float(c) for c, _ in self.samples), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(self.samples), "source": "NVML, sampled every ~4 ms from the first warm-up step to the end of the timed region"}
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
         self.tmp.flush()
         rows = []
         try:
@@ -177,7 +222,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(rows)}
+                "reasons": sorted(reasons), "samples": len(rows), "source": "nvidia-smi -lms 20"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -437,12 +482,14 @@ def run_workload(env: Env, a, workload: str, steps: int, warmup: int, *, headlin
     single_kernel = (world == 1 or fused)
 
     # ---- value: device-resident queries, one CUDA-event pair around K back-to-back searches ----
-    for s in range(warmup):
-        idx.search_device(q_all[s], k)
-    env.barrier()
     sampler = ClockSampler(env.local_rank) if headline else None
     if sampler and rank == 0:
         sampler.start()
+    for s in range(warmup):
+        idx.search_device(q_all[s], k)
+    env.barrier()
+    if sampler and rank == 0:
+        sampler.samples.clear()  # keep what is sampled under the timed load only
     launches0 = idx.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = []

@@ -43,9 +43,38 @@ _DTYPES = {"float32": np.float32, "int64": np.int64, "uint8": np.uint8, "bool": 
 _MAX_HEADER = 1 << 20
 
 
+def _private_dir(path: str) -> str:
+    """A directory only this user can enter (created 0700; an existing one must be ours and closed to others —
+    a predictable name in /tmp could otherwise be squatted by another local user)."""
+    try:
+        os.mkdir(path, 0o700)
+    except FileExistsError:
+        pass
+    st = os.lstat(path)
+    import stat as _stat
+
+    if not _stat.S_ISDIR(st.st_mode) or st.st_uid != os.getuid() or (st.st_mode & 0o077):
+        raise PermissionError(f"{path} is not a private directory of uid {os.getuid()}; set B200_RESIDENT_SOCKET")
+    return path
+
+
 def default_socket_path() -> str:
-    return os.environ.get("B200_RESIDENT_SOCKET") or os.path.join(
-        os.environ.get("XDG_RUNTIME_DIR") or "/tmp", f"b200-resident-{os.getuid()}.sock")
+    explicit = os.environ.get("B200_RESIDENT_SOCKET")
+    if explicit:
+        return explicit
+    run = os.environ.get("XDG_RUNTIME_DIR")  # per-user and 0700 by specification
+    if run and os.path.isdir(run):
+        return os.path.join(run, f"b200-resident-{os.getuid()}.sock")
+    return os.path.join(_private_dir(f"/tmp/b200-resident-{os.getuid()}"), "resident.sock")
+
+
+def _peer_uid(sock: socket.socket) -> int | None:
+    """uid of the process on the other end of a unix socket (SO_PEERCRED; None where unsupported)."""
+    try:
+        creds = sock.getsockopt(socket.SOL_SOCKET, socket.SO_PEERCRED, struct.calcsize("3i"))
+        return struct.unpack("3i", creds)[1]
+    except (AttributeError, OSError):
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -105,10 +134,11 @@ def recv_frame(sock: socket.socket):
 # service
 # ------------------------------------------------------------------------------------------------
 class _Entry:
-    __slots__ = ("index", "path", "stamp", "dirty", "last_used")
+    __slots__ = ("index", "path", "stamp", "dirty", "last_used", "holders")
 
     def __init__(self, index, path=None, stamp=None):
         self.index, self.path, self.stamp, self.dirty, self.last_used = index, path, stamp, False, time.monotonic()
+        self.holders = 0  # connections that hold a handle to this entry
 
 
 def _stamp(path: str):
@@ -174,9 +204,12 @@ class ResidentService:
         if e is None:
             raise RuntimeError("stale index handle")
         e.last_used = time.monotonic()
+        if op in ("add", "reset"):
+            e = self._own(table, int(a["h"]), e)  # mutations never show through another connection's handle
         idx = e.index
         if op == "release":
             del table[int(a["h"])]
+            e.holders -= 1
             return {}, ()
         if op == "ntotal":
             return {"ntotal": int(idx.ntotal)}, ()
@@ -216,10 +249,30 @@ class ResidentService:
             return {}, ()
         raise RuntimeError(f"unknown op {op!r}")
 
+    def _own(self, table: dict, h: int, e: _Entry) -> _Entry:
+        """Before a mutation: every process of the reference has a private copy of the index it read, so an unsaved
+        add / reset must not be visible to other connections.  A path-cached entry held by this connection alone is
+        taken out of the cache and mutated in place (no copy; write() puts it back); one that other connections also
+        hold is replaced, for this connection, by a private copy read from the file."""
+        if e.path is None or self.by_path.get(e.path) is not e:
+            if e.holders <= 1:
+                return e  # anonymous or already private
+        if e.holders <= 1:
+            if e.path is not None and self.by_path.get(e.path) is e:
+                del self.by_path[e.path]
+            return e
+        mine = _Entry(self.backend.read_index(e.path), e.path, _stamp(e.path))
+        self.stats["loads"] += 1
+        e.holders -= 1
+        mine.holders = 1
+        table[h] = mine
+        return mine
+
     @staticmethod
     def _register(table: dict, e: _Entry) -> dict:
         h = max(table, default=0) + 1
         table[h] = e
+        e.holders += 1
         idx = e.index
         metric = getattr(idx, "metric_type", getattr(getattr(idx, "index", None), "metric_type", METRIC_L2))
         return {"h": h, "d": int(idx.d), "metric": int(metric),
@@ -231,6 +284,9 @@ class _Handler(socketserver.BaseRequestHandler):
         svc: ResidentService = self.server.service
         table: dict = {}
         sock = self.request
+        uid = _peer_uid(sock)
+        if uid is not None and uid not in (os.getuid(), 0):
+            return  # the socket is 0600 in a private directory; this is the second lock on the same door
         try:
             while not svc.stopping:
                 frame = recv_frame(sock)
@@ -250,6 +306,8 @@ class _Handler(socketserver.BaseRequestHandler):
         except (ConnectionError, BrokenPipeError, OSError):
             pass
         finally:
+            for e in table.values():
+                e.holders -= 1
             table.clear()  # anonymous indexes die with their connection; path-cached ones stay resident
 
 
@@ -321,11 +379,17 @@ class ResidentClient:
         except OSError:
             s.close()
             raise
+        uid = _peer_uid(s)
+        if uid is not None and uid != os.getuid():
+            s.close()  # queries, vectors and file paths only go to a service of the same user
+            raise PermissionError(f"the service on {self.path} runs as uid {uid}, not {os.getuid()}")
         return s
 
     def _connect(self, autostart, timeout):
         try:
             return self._try(timeout)
+        except PermissionError:
+            raise
         except OSError as first:
             if not autostart:
                 raise ConnectionError(f"no resident service on {self.path}: {first}") from None

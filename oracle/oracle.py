@@ -198,13 +198,17 @@ def np_search_f64(metric: int, db: np.ndarray, q: np.ndarray, k: int, ids: np.nd
 
 
 def check_topk_against_truth(metric: int, db: np.ndarray, q: np.ndarray, D: np.ndarray, I: np.ndarray,
-                             rows_of_ids=None, rel_eps: float = 1e-5):
+                             rows_of_ids=None, rel_eps: float = 1e-5, abs_floor: float | None = None):
     """Adjudicated parity check of one result list against the fp64 truth (SURVEY.md §7 hard part 1).
 
-    Passes iff (a) every returned distance is within rel_eps of the fp64 score of its row, and
-    (b) the returned rows are a valid top-k: every row NOT returned has an fp64 score that is not
-    better than the worst returned one by more than rel_eps (relative), and the returned order is
-    best-first up to rel_eps.  Returns a list of human-readable violations (empty == pass).
+    Tolerance of a score with fp64 value t:  tol(t) = rel_eps * |t| + abs_floor.
+      rel_eps   1e-5, the relative tolerance north_star states for fp32 distances — applied PER ELEMENT to |t|;
+      abs_floor the explicit absolute term for scores near zero, where a relative bound is meaningless: by default
+                2^-24 * sum_i |q_i * y_i| bounded by 2^-24 * ||q|| * max||y|| (half an fp32 ulp of the largest
+                possible magnitude of the sum) — 6e-8 for unit vectors.
+    Passes iff (a) every returned distance is within tol of the fp64 score of its row, (b) the returned order is
+    best-first up to tol of the pair, and (c) the result is complete: no row outside it has an fp64 score better
+    than the worst returned one by more than tol.  Returns human-readable violations (empty == pass).
     """
     q = np.asarray(q, dtype=np.float32).reshape(-1)
     truth = scores_f64(metric, db, q)
@@ -217,22 +221,31 @@ def check_topk_against_truth(metric: int, db: np.ndarray, q: np.ndarray, D: np.n
         bad.append("duplicate rows in result")
     if len(got) != min(len(rows), db.shape[0]):
         bad.append(f"expected {min(len(rows), db.shape[0])} valid results, got {len(got)}")
-    scale = max(1.0, float(np.max(np.abs(truth))) if truth.size else 1.0)
-    tol = rel_eps * scale
+    if abs_floor is None:
+        qn = float(np.linalg.norm(q.astype(np.float64)))
+        yn = float(np.sqrt(np.max(np.einsum("ij,ij->i", db.astype(np.float64), db.astype(np.float64))))) if db.size else 0.0
+        mag = qn * yn if metric == METRIC_IP else (qn + yn) ** 2
+        abs_floor = 2.0 ** -24 * mag
+
+    def tol(t):
+        return rel_eps * abs(float(t)) + abs_floor
+
     for pos, (r, dist) in enumerate(zip(rows, np.asarray(D, dtype=np.float64))):
         if r < 0:
             continue
-        if abs(dist - truth[r]) > rel_eps * max(1.0, abs(truth[r])):
-            bad.append(f"pos {pos}: distance {dist} vs fp64 {truth[r]}")
+        if abs(dist - truth[r]) > tol(truth[r]):
+            bad.append(f"pos {pos}: distance {dist} vs fp64 {truth[r]} (tolerance {tol(truth[r])})")
     t = sign * truth[got]
-    if np.any(np.diff(t) < -tol):
-        bad.append("result not best-first within tolerance")
+    for j in range(1, len(t)):
+        if t[j] < t[j - 1] - tol(t[j - 1]):
+            bad.append(f"result not best-first within tolerance at position {j}")
+            break
     if len(got):
         worst = np.max(t)
         mask = np.ones(db.shape[0], dtype=bool)
         mask[got] = False
         if mask.any():
             best_out = np.min(sign * truth[mask])
-            if best_out < worst - tol:
+            if best_out < worst - tol(worst):
                 bad.append(f"a better row was left out: outside {best_out} vs worst kept {worst}")
     return bad

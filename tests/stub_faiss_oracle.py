@@ -38,7 +38,12 @@ class IndexFlat:
         self.rows = np.concatenate([self.rows, x], axis=0)
 
     def search(self, x, k, ids=None):
-        return oracle.search(self.metric_type, self.rows, x, k, ids=ids)
+        # STUB_FAISS_ORDER=device: the B200 kernels' summation order (bit-exact transcripts against the GPU shim);
+        # default: the faiss-like SIMD order
+        import os
+
+        order = oracle.ORDER_DEVICE if os.environ.get("STUB_FAISS_ORDER") == "device" else oracle.ORDER_SIMD
+        return oracle.search(self.metric_type, self.rows, x, k, ids=ids, order=order)
 
 
 class IndexFlatIP(IndexFlat):

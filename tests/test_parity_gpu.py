@@ -97,6 +97,69 @@ def test_matches_faiss_order_oracle_ids(b200, metric):
     np.testing.assert_allclose(D, Dw, rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("case", [
+    pytest.param(dict(n=1_000_000, d=768, metric=0, normalize=True, nq=8), id="1Mx768_cosine"),   # BASELINE config 1
+    pytest.param(dict(n=1_000_000, d=384, metric=1, normalize=False, nq=8), id="1Mx384_l2"),
+])
+def test_config1_size_against_faiss_order_oracle(b200, case):
+    """At BASELINE config-1 size against the SIMD-order restatement (the faiss-like summation, a different order
+    from the kernels'): ids exact, distances within 1e-5 relative per element — and the fp64 truth agrees."""
+    n, d, metric, nq, k = case["n"], case["d"], case["metric"], case["nq"], 10
+    oracle.set_threads(max(1, len(__import__("os").sched_getaffinity(0))))
+    db = oracle.synth_rows(n, d, 1234)
+    q = oracle.synth_rows(nq, d, 5678)
+    if case["normalize"]:
+        db, q = oracle.normalize_rows(db), oracle.normalize_rows(q)
+    idx = make_index(b200, metric, d, db)
+    D = np.empty((nq, k), np.float32)
+    I = np.empty((nq, k), np.int64)
+    for i in range(nq):  # one query per call: the latency path (K2), as config 1 is quoted
+        D[i], I[i] = (a[0] for a in idx.search(q[i:i + 1], k))
+    Dw, Iw = oracle.search(metric, db, q, k, order=oracle.ORDER_SIMD, rowpar=True)
+    np.testing.assert_array_equal(I, Iw)
+    np.testing.assert_allclose(D, Dw, rtol=1e-5, atol=0)
+    for i in range(2):
+        assert oracle.check_topk_against_truth(metric, db, q[i], D[i], I[i]) == []
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_near_tie_dataset_adjudicated_by_fp64(b200, metric):
+    """Adversarial near ties: the candidates' scores are spaced 1-4 fp32 ulps apart (plus exact duplicates), so two
+    correct fp32 summation orders may rank them differently.  The GPU must (a) equal the oracle's restatement of its
+    own order bit for bit, (b) pass the fp64 adjudication at 1e-5 relative, (c) equal the SIMD-order ranking up to
+    groups of near-tied scores, (d) order exact ties by row."""
+    d, k = 256, 64
+    rng = np.random.default_rng(7)
+    v = rng.standard_normal(d).astype(np.float32)
+    v /= np.linalg.norm(v)
+    qv = (v + 0.05 * rng.standard_normal(d).astype(np.float32)).astype(np.float32)
+    n_tie = 200
+    steps = rng.integers(1, 5, size=n_tie).cumsum()           # 1..4 ulp increments
+    scale = (1.0 + steps.astype(np.float64) * 2.0 ** -23).astype(np.float32)
+    ties = (v[None, :].astype(np.float64) * scale[:, None].astype(np.float64)).astype(np.float32)
+    filler = oracle.synth_rows(20_000, d, 77) * 0.01           # far from the query either way
+    db = np.concatenate([filler[:7000], ties, filler[7000:], ties[:50]])  # + 50 exact duplicates at the end
+    q = qv[None, :]
+    if metric == 1:
+        q = (2.0 * v)[None, :]  # L2 to scale*v is (2 - scale)^2: ~1, spaced ~2 ulps; the filler sits at ~4
+    idx = make_index(b200, metric, d, db)
+    D, I = idx.search(q, k)
+    Dw, Iw = oracle.search(metric, db, q, k, order=oracle.ORDER_DEVICE)
+    np.testing.assert_array_equal(I, Iw)
+    np.testing.assert_array_equal(D, Dw)
+    assert oracle.check_topk_against_truth(metric, db, q[0], D[0], I[0]) == []
+    Ds, Is = oracle.search(metric, db, q, k, order=oracle.ORDER_SIMD)
+    eps = 1e-5 * float(np.max(np.abs(Ds)))
+    # the k-boundary may cut a near-tie group: compare the groups that lie entirely inside the list
+    cut = k
+    while cut > 0 and abs(float(Ds[0, cut - 1]) - float(Ds[0, k - 1])) <= eps:
+        cut -= 1
+    assert_same_ranking_mod_near_ties(list(I[0, :cut]), list(Is[0, :cut]), Ds[0, :cut], eps)
+    for j in range(1, k):  # exact ties: smaller row first
+        if D[0, j] == D[0, j - 1]:
+            assert I[0, j] > I[0, j - 1]
+
+
 @pytest.mark.parametrize("variant", ["bulk", "ldg"])
 @pytest.mark.parametrize("metric", [0, 1])
 def test_exact_ties_and_boundary(b200, variant, metric):
@@ -238,10 +301,11 @@ def test_synthetic_rows_bit_identical_to_oracle(b200):
 @pytest.mark.parametrize("metric", [0, 1])
 @pytest.mark.parametrize("variant", ["bulk", "ldg"])
 def test_bf16_storage_bit_exact_and_recall(b200, metric, variant):
-    n, d, k, nq = 30000, 1024, 10, 8
+    n, d, k, nq = 30000, 1024, 10, 64  # 640 result slots: one miss costs 0.0016 of recall
     db = oracle.normalize_rows(oracle.synth_rows(n, d, 1234))
     q = oracle.normalize_rows(oracle.synth_rows(nq, d, 5678))
     idx = make_index(b200, metric, d, db, store="bf16", variant=variant)
+    idx.set_option("gemm_min_nq", 0)  # the scan kernel in both variants (batches would go to the tensor-core path)
     D, I = idx.search(q, k)
     db16 = oracle.round_bf16(db)
     Dw, Iw = oracle.search(metric, db16, q, k, order=oracle.ORDER_DEVICE, chunk=8)
@@ -250,7 +314,7 @@ def test_bf16_storage_bit_exact_and_recall(b200, metric, variant):
     # bf16 storage is lossy: report recall@k against the fp32 oracle instead of id equality
     _, I32 = oracle.search(metric, db, q, k)
     recall = np.mean([len(set(I[i]) & set(I32[i])) / k for i in range(nq)])
-    assert recall >= 0.8, recall
+    assert recall >= 0.99, recall  # measured 0.996-1.0 at 10M x 1024 (bench.py reports it per run)
 
 
 @pytest.mark.parametrize("metric", [0, 1])

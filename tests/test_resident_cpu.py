@@ -296,3 +296,66 @@ def test_concurrent_clients_are_serialised_correctly(service, tmp_path):
     assert not errors, errors
     st = service.stats()
     assert st["loads"] == 0 and st["hits"] == 6
+
+
+def test_unsaved_mutations_are_private_to_their_connection(service, tmp_path):
+    """Every process of the reference holds a private copy of the index it read.  Two connections that opened the
+    same cached file: an add on one is invisible to the other until it is written; a sole holder mutates in place
+    (no reload) and the entry returns to the cache on write."""
+    d = 16
+    x = _rows(40, d, 3)
+    ids = np.arange(40, dtype=np.int64)
+    path = str(tmp_path / "shared.memo")
+    first = resident.IndexIDMap2(resident.IndexHNSWFlat(d, 32))
+    first.add_with_ids(x[:30], ids[:30])
+    resident.write_index(first, path)
+
+    a_conn = service.new_process()
+    a = resident.read_index(path)
+    b_conn = service.new_process()
+    b = resident.read_index(path)
+    assert a.ntotal == 30 and b.ntotal == 30
+    loads_before = service.stats()["loads"]
+    resident.set_client(a_conn)
+    a.add_with_ids(x[30:35], ids[30:35])          # shared entry: a gets a private copy
+    assert a.ntotal == 35
+    resident.set_client(b_conn)
+    assert b.ntotal == 30                          # b still sees what it read
+    Db, Ib = b.search(x[31:32], 1)
+    assert Ib[0, 0] != 31
+    c_conn = service.new_process()
+    c = resident.read_index(path)                  # a fresh process reads the file: 30 rows
+    assert c.ntotal == 30
+    assert service.stats()["loads"] == loads_before + 1   # the private copy; c and b share the cached entry
+    resident.set_client(a_conn)
+    resident.write_index(a, path)
+    d_conn = service.new_process()
+    dd = resident.read_index(path)
+    assert dd.ntotal == 35
+    for cn in (a_conn, b_conn, c_conn, d_conn):
+        cn.close()
+
+    # sole holder: in place, no extra load
+    e_conn = service.new_process()
+    e = resident.read_index(path)
+    loads = service.stats()["loads"]
+    e.add_with_ids(x[35:], ids[35:])
+    assert e.ntotal == 40 and service.stats()["loads"] == loads
+    f_conn = service.new_process()
+    f = resident.read_index(path)                  # the dirty entry left the cache: the file is the truth
+    assert f.ntotal == 35
+    e_conn.close()
+    f_conn.close()
+
+
+def test_default_socket_lives_in_a_private_directory(monkeypatch, tmp_path):
+    monkeypatch.delenv("B200_RESIDENT_SOCKET", raising=False)
+    monkeypatch.delenv("XDG_RUNTIME_DIR", raising=False)
+    p = resident.default_socket_path()
+    st = os.stat(os.path.dirname(p))
+    assert st.st_uid == os.getuid() and (st.st_mode & 0o077) == 0
+    open_dir = tmp_path / "open"
+    open_dir.mkdir(mode=0o755)
+    os.chmod(open_dir, 0o755)
+    with pytest.raises(PermissionError):
+        resident._private_dir(str(open_dir))
