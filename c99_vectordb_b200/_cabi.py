@@ -72,6 +72,7 @@ SIGNATURES = [
     ("b200_normalize_rows", C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int]),
     ("b200_merge_topk_dev", C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("b200_hash_embed", C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    ("b200_index_add_texts", C.c_int, [_h, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, _ip]),
     ("b200_py_hash_seed0", C.c_int64, [C.c_char_p, C.c_int64]),
     ("b200_synth_rows_dev", C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
 ]

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "embed_dev.cuh"
 #include "fullrank.cuh"
 #include "gemm_topk.cuh"
 #include "merge.cuh"
@@ -80,6 +81,12 @@ struct b200_index {
     unsigned long long* stamps = nullptr;  // [grid, 8] phase stamps of the last scan launch (option scan_phase_stamps)
     size_t stamps_cap = 0;
     int stamps_grid = 0;
+    uint8_t* txt_dev[2] = {nullptr, nullptr};  // device staging of text chunks (K6)
+    size_t txt_cap = 0;
+    uint8_t* txt_keep = nullptr;
+    uint32_t* txt_blocks = nullptr;
+    unsigned long long* txt_rowbase = nullptr;
+    size_t txt_rec_cap = 0;
     cudaStream_t last_stream = nullptr;  // the stream the handle's scratch was last used on
     cudaEvent_t order_ev = nullptr;
     float* q_dev = nullptr;   // staged host queries
@@ -259,6 +266,10 @@ extern "C" int b200_index_destroy(b200_index* ix) {
     cudaFree(ix->partials);
     cudaFree(ix->ctl);
     cudaFree(ix->stamps);
+    for (int i = 0; i < 2; ++i) cudaFree(ix->txt_dev[i]);
+    cudaFree(ix->txt_keep);
+    cudaFree(ix->txt_blocks);
+    cudaFree(ix->txt_rowbase);
     if (ix->order_ev) cudaEventDestroy(ix->order_ev);
     cudaFree(ix->q_dev);
     cudaFree(ix->qn_dev);
@@ -947,6 +958,130 @@ extern "C" int b200_index_load(b200_index** out, const char* path, int store, in
     }
     if (info.kind && info.ntotal == 0) ix->ids_state = 1;  // an empty id-mapped index stays id-mapped
     *out = ix;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: bulk rebuild from texts — hashing-trick embedder + K1 on the device (embed_dev.cuh)
+// ---------------------------------------------------------------------------------------------
+extern "C" int b200_index_add_texts(b200_index* ix, const char* utf8_host, const int64_t* offsets_host, int64_t n,
+                                    const int64_t* ids_host, int64_t first_id, int skip_blank, int normalize, int with_ids,
+                                    int64_t* n_added) {
+    if (!ix) return fail("null index");
+    if (n < 0) return fail("negative n");
+    if (n_added) *n_added = 0;
+    if (n == 0) return 0;
+    if (!utf8_host || !offsets_host) return fail("null buffer");
+    if (ix->d > EMB_MAX_DIM) return fail("the device embedder supports d <= %d, the index has d = %d", EMB_MAX_DIM, ix->d);
+    for (int64_t i = 0; i < n; ++i)
+        if (offsets_host[i + 1] < offsets_host[i]) return fail("offsets must be non-decreasing (record %lld)", (long long)i);
+    const bool want_ids = with_ids != 0 || ids_host != nullptr;
+    CKI(use_device(ix));
+    CKI(order_after_previous_stream(ix, ix->stream));
+    CKI(note_ids(ix, want_ids));
+    CKI(ensure_capacity(ix, ix->ntotal + n, want_ids));  // worst case: nothing is blank
+    cudaStream_t st = ix->stream;
+    // chunks of whole records: <= 32 MB of text and <= 2^20 records, through the double-buffered pinned ring
+    const size_t kTextChunk = (size_t)32 << 20;
+    const int64_t kRecChunk = (int64_t)1 << 20;
+    size_t max_rec = 0;
+    for (int64_t i = 0; i < n; ++i) max_rec = std::max(max_rec, (size_t)(offsets_host[i + 1] - offsets_host[i]));
+    const size_t text_cap = std::max(kTextChunk, max_rec) + 64;
+    const size_t buf_bytes = text_cap + (size_t)(kRecChunk + 1) * 8 + (size_t)kRecChunk * 8 + 64;
+    CKI(ensure_pinned_ring(ix, buf_bytes));
+    if (ix->txt_cap < buf_bytes) {
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < 2; ++i) {
+            if (ix->txt_dev[i]) CK(cudaFree(ix->txt_dev[i]));
+            ix->txt_dev[i] = nullptr;
+        }
+        ix->txt_cap = 0;
+        for (int i = 0; i < 2; ++i) CK(cudaMalloc((void**)&ix->txt_dev[i], buf_bytes));
+        ix->txt_cap = buf_bytes;
+    }
+    const size_t max_blocks = (size_t)((kRecChunk + EMB_BLOCK_RECS - 1) / EMB_BLOCK_RECS);
+    if (ix->txt_rec_cap < (size_t)kRecChunk) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(ix->txt_keep);
+        cudaFree(ix->txt_blocks);
+        ix->txt_keep = nullptr;
+        ix->txt_blocks = nullptr;
+        ix->txt_rec_cap = 0;
+        CK(cudaMalloc((void**)&ix->txt_keep, (size_t)kRecChunk));
+        CK(cudaMalloc((void**)&ix->txt_blocks, (max_blocks + 1) * sizeof(uint32_t)));
+        ix->txt_rec_cap = (size_t)kRecChunk;
+    }
+    if (!ix->txt_rowbase) CK(cudaMalloc((void**)&ix->txt_rowbase, sizeof(unsigned long long)));
+    const unsigned long long start_row = (unsigned long long)ix->ntotal;
+    CK(cudaMemcpyAsync(ix->txt_rowbase, &start_row, sizeof start_row, cudaMemcpyHostToDevice, st));
+    const int dim_s = (ix->d_pad + 3) & ~3;
+    const size_t esmem = (size_t)(EMB_THREADS / 32) * dim_s * sizeof(float);
+    CK(cudaFuncSetAttribute(text_embed_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+    CK(cudaFuncSetAttribute(text_embed_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+    const int threads = staging_threads();
+    int b = 0;
+    int64_t r0 = 0;
+    while (r0 < n) {
+        // the records of this chunk
+        int64_t r1 = r0;
+        const int64_t byte0 = offsets_host[r0];
+        while (r1 < n && r1 - r0 < kRecChunk && (size_t)(offsets_host[r1 + 1] - byte0) <= text_cap - 64) ++r1;
+        if (r1 == r0) return fail("record %lld does not fit the text staging buffer", (long long)r0);  // cannot happen: text_cap >= max_rec
+        const int64_t cnt = r1 - r0;
+        const size_t tbytes = (size_t)(offsets_host[r1] - byte0);
+        const size_t off_offsets = (tbytes + 15) & ~(size_t)15;
+        const size_t off_ids = off_offsets + (size_t)(cnt + 1) * 8;
+        const size_t total = off_ids + (ids_host ? (size_t)cnt * 8 : 0);
+        CK(cudaEventSynchronize(ix->up_ev[b]));  // the DMA that last read this pinned buffer is done
+        uint8_t* pin = ix->up_pin[b];
+        parallel_memcpy(pin, reinterpret_cast<const uint8_t*>(utf8_host) + byte0, tbytes, threads);
+        int64_t* po = reinterpret_cast<int64_t*>(pin + off_offsets);
+        for (int64_t i = 0; i <= cnt; ++i) po[i] = offsets_host[r0 + i] - byte0;
+        if (ids_host) memcpy(pin + off_ids, ids_host + r0, (size_t)cnt * 8);
+        uint8_t* dev = ix->txt_dev[b];
+        CK(cudaMemcpyAsync(dev, pin, total, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ix->up_ev[b], st));
+        TextParams p;
+        memset(&p, 0, sizeof p);
+        p.text = dev;
+        p.offsets = reinterpret_cast<const int64_t*>(dev + off_offsets);
+        p.n = (uint32_t)cnt;
+        p.skip_blank = skip_blank;
+        p.keep = ix->txt_keep;
+        p.block_count = ix->txt_blocks;
+        p.dim = ix->d;
+        p.d_pad = ix->d_pad;
+        p.store = ix->store;
+        p.normalize = normalize;
+        p.rows = ix->rows;
+        p.pitch_bytes = ix->pitch;
+        p.ids = want_ids ? ix->ids : nullptr;
+        p.ids_in = ids_host ? reinterpret_cast<const int64_t*>(dev + off_ids) : nullptr;
+        p.first_id = first_id + r0;
+        p.row_base = ix->txt_rowbase;
+        const uint32_t blocks = (uint32_t)((cnt + EMB_BLOCK_RECS - 1) / EMB_BLOCK_RECS);
+        CK(cudaMemsetAsync(ix->txt_blocks + blocks, 0, sizeof(uint32_t), st));  // becomes the chunk total after the scan
+        text_classify_kernel<<<blocks, EMB_THREADS, 0, st>>>(p);
+        radix_scan_kernel<<<1, 1024, 0, st>>>(ix->txt_blocks, (uint64_t)blocks + 1);
+        if (ix->store == B200_STORE_F32) text_embed_kernel<0><<<blocks, EMB_THREADS, esmem, st>>>(p);
+        else text_embed_kernel<1><<<blocks, EMB_THREADS, esmem, st>>>(p);
+        text_advance_kernel<<<1, 32, 0, st>>>(ix->txt_rowbase, ix->txt_blocks, blocks);
+        ix->launches += 4;
+        CK(cudaGetLastError());
+        r0 = r1;
+        b ^= 1;
+    }
+    unsigned long long end_row = 0;
+    CK(cudaMemcpyAsync(&end_row, ix->txt_rowbase, sizeof end_row, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_added) *n_added = (int64_t)(end_row - start_row);
+    if (end_row != start_row) {
+        ix->ntotal = (int64_t)end_row;
+        ix->sh_valid_rows = -1;
+        ix->ids_minmax_rows = -1;
+    } else if (ix->ntotal == 0) {
+        ix->ids_state = 0;  // nothing was added: the index stays undecided
+    }
     return 0;
 }
 

@@ -70,6 +70,28 @@ def pack_row_mask(row_mask, ntotal: int) -> np.ndarray:
     return np.packbits(padded, bitorder="little").view("<u4").copy()
 
 
+def pack_texts(texts, ids=None, skip_blank: bool = True):
+    """Records -> (utf-8 blob, int64 offsets[n+1], kept ids or None).  ASCII corpora travel as they are (one join, one
+    encode; the device lower-cases and skips blank records).  Anything else is lower-cased with Python's Unicode rules
+    per record, blank records (str.isspace semantics of memo_cli.py:136-142) are dropped here, and the ids of the
+    kept records are returned explicitly."""
+    texts = ["" if t is None else t for t in texts]
+    n = len(texts)
+    joined = "\n".join(texts)
+    if joined.isascii():
+        blob = joined.encode("ascii")
+        offsets = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.fromiter(map(len, texts), dtype=np.int64, count=n) + 1, out=offsets[1:])
+        offsets[n] = len(blob)  # the last record has no trailing "\n"; the separators inside the ranges are white space
+        return blob, offsets, None
+    base_ids = np.arange(n, dtype=np.int64) if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+    keep = [i for i, t in enumerate(texts) if not (skip_blank and (t == "" or t.isspace()))]
+    low = [texts[i].lower().encode("utf-8") for i in keep]
+    offsets = np.zeros(len(keep) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in low], out=offsets[1:])
+    return b"".join(low), offsets, base_ids[keep]
+
+
 class Index:
     """Common base (faiss.Index)."""
 
@@ -173,6 +195,22 @@ class IndexFlat(Index):
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         assert ids.shape == (x.shape[0],), "not same number of vectors and ids"
         _cabi.check(_cabi.load().b200_index_add(self._h, x.ctypes.data, x.shape[0], ids.ctypes.data, int(self.normalize)))
+
+    def _add_texts(self, blob: bytes, offsets: np.ndarray, ids: np.ndarray | None, first_id: int, skip_blank: bool,
+                   with_ids: bool) -> int:
+        """K6 (b200_index_add_texts): records = byte ranges of `blob`; embedded, normalised and stored on the device.
+        Returns the number of rows added."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.shape[0] - 1
+        idp = None
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+            assert ids.shape == (n,), "not same number of texts and ids"
+            idp = ids.ctypes.data
+        added = C.c_int64(0)
+        _cabi.check(_cabi.load().b200_index_add_texts(self._h, blob, offsets.ctypes.data, n, idp, int(first_id), int(skip_blank),
+                                                      1, int(with_ids), C.byref(added)))
+        return int(added.value)
 
     def add_synthetic(self, n: int, seed: int, first_row: int = 0, *, with_ids: bool = False, first_id: int = 0) -> None:
         """Rows u(seed,row,col) generated on the device; for databases too large to upload."""
@@ -291,6 +329,16 @@ class IndexIDMap(Index):
 
     def add_with_ids(self, x, ids) -> None:
         self.index._add_with_ids(x, ids)
+
+    def add_texts(self, texts, ids=None, *, skip_blank: bool = True) -> int:
+        """Extension: embed_text_hash + normalize + add_with_ids of every record on the device — the
+        whole of rebuild_index_from_texts (memo_cli.py:272-285) in one call.  ids default to the records' positions in
+        `texts` (what the reference assigns, :276-282); blank records are skipped as there.  Token hashes are CPython's
+        under PYTHONHASHSEED=0 (reproducible across processes).  Returns the number of rows added."""
+        blob, offsets, keep_ids = pack_texts(texts, ids, skip_blank)
+        if keep_ids is None:  # plain ASCII: blank detection and ASCII lower-casing happen on the device
+            return self.index._add_texts(blob, offsets, ids, 0, skip_blank, True)
+        return self.index._add_texts(blob, offsets, keep_ids, 0, False, True)
 
     def add(self, x) -> None:
         raise RuntimeError("add does not make sense with IndexIDMap, use add_with_ids")  # as faiss

@@ -143,8 +143,13 @@ def rebuild_index_from_texts(texts: Iterable[str | None], verbose: bool = False,
     """memo_cli.py:272-285: full rebuild; blank records are skipped so ids may be sparse.  One bulk
     add.  `vectors` (unit rows for the kept records, in order) bypasses the host embedder."""
     texts = list(texts)
-    keep = [i for i, t in enumerate(texts) if not is_blank_body(t or "")]
     idx = create_index(dim, metric)
+    if hash_fn is None and vectors is None:
+        # stable hash: the whole rebuild — tokenise, hash, bucket, normalise, add — is one device pipeline (K6);
+        # only the text bytes cross PCIe
+        idx.add_texts(texts)
+        return idx
+    keep = [i for i, t in enumerate(texts) if not is_blank_body(t or "")]
     if keep:
         if vectors is None:
             rows = embed_texts([texts[i] or "" for i in keep], dim, hash_fn)

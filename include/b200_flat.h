@@ -238,6 +238,17 @@ int b200_merge_topk_dev(int metric, int G, int64_t nq, int64_t k, const float* D
  * un-normalised bucket counts.  b200_py_hash_seed0 is the token hash itself. */
 int b200_hash_embed(const char* utf8, const int64_t* offsets, int64_t n, int dim, float* out);
 int64_t b200_py_hash_seed0(const char* bytes, int64_t len);
+/* K6 — bulk rebuild from texts on the device (replaces rebuild_index_from_texts, memo_cli.py:272-285, and the
+ * embed_text_hash + normalize of every record, memo_cli.py:131-135,:158-167): the text bytes are uploaded in chunks
+ * of whole records, one warp per record tokenises ([a-z0-9_]+ after ASCII lower-casing; lower-case non-ASCII text
+ * with Unicode rules first), hashes every token (CPython SipHash-1-3, PYTHONHASHSEED=0 key), accumulates the
+ * signed buckets in shared memory, normalises with K1's arithmetic (normalize != 0) and stores the row straight
+ * into the index.  skip_blank != 0 leaves out records that hold nothing but ASCII white space, as the reference's
+ * rebuild does; kept rows stay in record order.  ids: ids_host[i], or first_id + i (the record's position) when
+ * ids_host is NULL and with_ids != 0, or none (add() semantics) when both are 0.  n_added receives the rows added. */
+int b200_index_add_texts(b200_index* ix, const char* utf8_host, const int64_t* offsets_host, int64_t n,
+                         const int64_t* ids_host, int64_t first_id, int skip_blank, int normalize, int with_ids,
+                         int64_t* n_added);
 /* counter-based synthetic rows written to a device buffer [n,d] float32 */
 int b200_synth_rows_dev(float* out_dev, int64_t n, int d, uint64_t seed, int64_t first_row,
                         int normalize, void* stream);

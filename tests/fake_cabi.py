@@ -110,6 +110,33 @@ class FakeLib:
         I = _arr(ids, n, C.c_int64, np.int64) if ids else None
         return self._append(ix, X, I, normalize)
 
+    def b200_index_add_texts(self, h, blob, offsets, n, ids, first_id, skip_blank, normalize, with_ids, n_added_ref):
+        """Host restatement of K6 for the CPU tests of pack_texts / add_texts: ASCII lower-casing, blank = only ASCII
+        white space, buckets from the library's own host embedder (b200_hash_embed)."""
+        ix = self._ix(h)
+        off = _arr(offsets, n + 1, C.c_int64, np.int64)
+        data = bytes(blob)
+        recs = [data[off[i]:off[i + 1]] for i in range(n)]
+        space = set(b"\t\n\x0b\x0c\r\x1c\x1d\x1e\x1f ")
+        keep = [i for i, r in enumerate(recs) if not (skip_blank and all(c in space for c in r))]
+        low = [bytes(c + 32 if 65 <= c <= 90 else c for c in recs[i]) for i in keep]
+        o2 = np.zeros(len(keep) + 1, dtype=np.int64)
+        np.cumsum([len(b) for b in low], out=o2[1:])
+        out = np.zeros((len(keep), ix.d), dtype=np.float32)
+        if keep:
+            rc = self._real.b200_hash_embed(b"".join(low), o2.ctypes.data, len(keep), ix.d, out.ctypes.data)
+            if rc:
+                return self._fail("b200_hash_embed failed")
+        I = None
+        if ids:
+            I = _arr(ids, n, C.c_int64, np.int64)[keep]
+        elif with_ids:
+            I = np.asarray(keep, dtype=np.int64) + first_id
+        n_added_ref._obj.value = len(keep)
+        if not keep:
+            return 0
+        return self._append(ix, out, I, normalize)
+
     def b200_index_add_file(self, h, path, rows_off, n, ids_off, normalize):
         ix = self._ix(h)
         size = os.path.getsize(path)

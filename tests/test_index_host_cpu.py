@@ -176,3 +176,32 @@ def test_memo_adapter_against_reference_golden_on_cpu():
             if i == len(ids_ref) or abs(float(sc_ref[i]) - float(sc_ref[i - 1])) > 2e-6:
                 assert sorted(got[start:i]) == sorted(np.asarray(ids_ref[start:i]).tolist())
                 start = i
+
+
+def test_add_texts_host_side_packs_and_skips_blanks():
+    """pack_texts / IndexIDMap2.add_texts (the host half of K6): ASCII corpora travel as one blob with the blank
+    detection left to the engine, non-ASCII corpora are lower-cased and filtered per record; either way the rows and
+    ids equal the reference-shaped rebuild with the stable hash injected."""
+    ascii_texts = ["Peanuts ALLERGY note", "", "   \t\n", "wifi password hunter2", None, "!!! ...", "snake_case x1 X1"]
+    uni_texts = ["café Kelvin K", "  ", "Straße ÄÖÜ", "", "plain ascii too"]
+    for texts in (ascii_texts, uni_texts):
+        idx = ma.create_index()
+        added = idx.add_texts(texts)
+        want_keep = [i for i, t in enumerate(texts) if not ma.is_blank_body(t or "")]
+        assert added == len(want_keep) == idx.ntotal
+        np.testing.assert_array_equal(ix.vector_to_array(idx.id_map), np.asarray(want_keep, dtype=np.int64))
+        raw = ma.embed_texts([texts[i] or "" for i in want_keep], hash_fn=ma.stable_hash)
+        nrm = np.sqrt((raw.astype(np.float64) ** 2).sum(axis=1, keepdims=True))
+        want = np.where(nrm <= 1e-8, 0, raw / np.maximum(nrm, 1e-30)).astype(np.float32)
+        np.testing.assert_array_equal(idx.index.reconstruct_n(0, idx.ntotal), want)
+    blob, offsets, keep_ids = ix.pack_texts(ascii_texts)
+    assert keep_ids is None and offsets[0] == 0 and offsets[-1] == len(blob) and len(offsets) == len(ascii_texts) + 1
+    blob, offsets, keep_ids = ix.pack_texts(uni_texts)
+    assert keep_ids.tolist() == [0, 2, 4] and blob.decode("utf-8").startswith("café kelvin k")
+    # explicit ids travel with the kept records
+    idx = ma.create_index()
+    idx.add_texts(["a b", " ", "c"], ids=np.array([10, 11, 12]))
+    assert ix.vector_to_array(idx.id_map).tolist() == [10, 12]
+    # the stable-hash rebuild is this one call
+    idx2 = ma.rebuild_index_from_texts(ascii_texts, hash_fn=None)
+    assert ix.vector_to_array(idx2.id_map).tolist() == [0, 3, 5, 6]
