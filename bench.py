@@ -496,7 +496,7 @@ def run_workload(env: Env, a, workload: str, steps: int, warmup: int, *, headlin
     ev0.record()
     for s in range(steps):
         q = q_all[warmup + s]
-        if single_kernel:
+        if single_kernel or nq > 1:  # batches: K3 per shard + one all-gather + merge/certificate (sharded.py)
             idx.search_device(q, k)
         else:
             # NCCL exchange: time the scan launches alone for the roofline, the whole step for the metric
@@ -640,8 +640,9 @@ def run_workload(env: Env, a, workload: str, steps: int, warmup: int, *, headlin
                             "whole_step_tflops": 2.0 * nq * n * d / (total_ms / steps * 1e-3) / 1e12,
                             "pass1_ms": base.get_option("stat_gemm_pass1_us") / 1e3,
                             "rerank_ms": base.get_option("stat_gemm_rerank_us") / 1e3,
-                            "uncertified_queries_recomputed": base.get_option("stat_gemm_fallbacks"),
-                            "candidates_per_query": base.get_option("stat_gemm_cand_total") / nq,
+                            "uncertified_queries_recomputed": (base.get_option("stat_gemm_fallbacks") if world == 1
+                                                               else idx.last_batch_uncertified),
+                            "candidates_per_query": (base.get_option("stat_gemm_cand_total") / nq if world == 1 else None),
                             "note": "bf16 tensor-core pass (tcgen05, TMEM accumulators) + exact fp32 re-rank; "
                                     "launch time is the kernel's own CUDA-event bracket from the last step"}
     idx.local.index.close()

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -112,7 +113,8 @@ struct b200_index {
     int64_t opt_gemm_min_rows = 4096, opt_gemm_min_nq = 2, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2;
     // read-only statistics of the last batched (K3) search
     int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
-            stat_gemm_pass2_us = 0, stat_gemm_rerank_us = 0, stat_gemm_scan_fallbacks = 0;
+            stat_gemm_pass2_us = 0, stat_gemm_rerank_us = 0, stat_gemm_scan_fallbacks = 0, stat_gemm_pre_us = 0,
+            stat_gemm_host_us = 0;
     // K3 state
     __nv_bfloat16* sh_rows = nullptr;  // bf16 shadow of the rows [ntotal, kpad]
     float* sh_norm2 = nullptr;
@@ -128,7 +130,8 @@ struct b200_index {
     uint32_t* g_cand = nullptr;
     int* g_cert = nullptr;
     size_t g_qb_cap = 0, g_q_cap = 0, g_tilemax_cap = 0, g_cand_cap = 0;
-    cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // pass brackets of the last batched search
+    cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // pass brackets of the last batched search
+    bool g_ev_pending = false;  // the brackets of an un-synchronised (row-sharded) batch have not been read yet
     uint8_t* up_pin[2] = {nullptr, nullptr};  // pinned upload ring for bulk host adds
     cudaEvent_t up_ev[2] = {nullptr, nullptr};
     size_t up_chunk = 0;
@@ -298,7 +301,7 @@ extern "C" int b200_index_destroy(b200_index* ix) {
     cudaFree(ix->g_count);
     cudaFree(ix->g_cand);
     cudaFree(ix->g_cert);
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 5; ++i)
         if (ix->g_ev[i]) cudaEventDestroy(ix->g_ev[i]);
     if (ix->xchg_status_host) cudaFreeHost((void*)ix->xchg_status_host);
     if (ix->pin) cudaFreeHost(ix->pin);
@@ -394,6 +397,8 @@ static const OptName kOpts[] = {
     {"stat_gemm_pass1_us", &b200_index::stat_gemm_pass1_us},
     {"stat_gemm_pass2_us", &b200_index::stat_gemm_pass2_us},
     {"stat_gemm_rerank_us", &b200_index::stat_gemm_rerank_us},
+    {"stat_gemm_pre_us", &b200_index::stat_gemm_pre_us},
+    {"stat_gemm_host_us", &b200_index::stat_gemm_host_us},
     {"fullrank_min_k", &b200_index::opt_fullrank_min_k},
     {"normalize_queries", &b200_index::opt_normalize_queries},
     {"host_staged_results", &b200_index::opt_staged_results},
@@ -409,6 +414,16 @@ extern "C" int b200_index_set_option(b200_index* ix, const char* name, int64_t v
 }
 extern "C" int b200_index_get_option(b200_index* ix, const char* name, int64_t* out_value) {
     if (!ix || !name || !out_value) return fail("null argument");
+    if (ix->g_ev_pending && strncmp(name, "stat_gemm_", 10) == 0 && ix->g_ev[3] && cudaEventQuery(ix->g_ev[3]) == cudaSuccess) {
+        // pass brackets of a row-sharded batch, read once its stream got there
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ix->g_ev[0], ix->g_ev[1]) == cudaSuccess) ix->stat_gemm_pass1_us = (int64_t)(ms * 1e3);
+        if (cudaEventElapsedTime(&ms, ix->g_ev[1], ix->g_ev[2]) == cudaSuccess) ix->stat_gemm_pass2_us = (int64_t)(ms * 1e3);
+        if (cudaEventElapsedTime(&ms, ix->g_ev[2], ix->g_ev[3]) == cudaSuccess) ix->stat_gemm_rerank_us = (int64_t)(ms * 1e3);
+        if (cudaEventElapsedTime(&ms, ix->g_ev[4], ix->g_ev[0]) == cudaSuccess) ix->stat_gemm_pre_us = (int64_t)(ms * 1e3);
+        ix->g_ev_pending = false;
+    }
+    cudaGetLastError();
     for (const OptName& o : kOpts)
         if (strcmp(o.name, name) == 0) {
             *out_value = ix->*(o.field);
@@ -1571,19 +1586,37 @@ static int ensure_shadow(b200_index* ix, cudaStream_t st) {
 static int search_scan_block(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev, int64_t* I_dev,
                              cudaStream_t st);
 
+// bound_out != nullptr selects the row-sharded form (b200_index_search_shard_dev): this index is one of `world`
+// shards, thresholds aim at 1/world of the candidates, the re-rank leaves each query's exclusion bound in
+// bound_out[nq] and nothing is read back — the certificate is taken after the merge over all shards.
 static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev, int64_t* I_dev,
-                       cudaStream_t st, int depth = 0) {
+                       cudaStream_t st, int depth = 0, float* bound_out = nullptr, int world = 1) {
     const int kpad = gemm_kpad(ix);
     const uint64_t n = (uint64_t)ix->ntotal;
     const uint32_t NT = (uint32_t)((n + G3_BLOCK_N - 1) / G3_BLOCK_N);
     const uint32_t m_tiles = (uint32_t)((nq + G3_BLOCK_M - 1) / G3_BLOCK_M);
     const uint32_t cap = 4096;
     const int cg = ix->opt_gemm_cta_group == 1 ? 1 : 2;
+    const auto host_t0 = std::chrono::steady_clock::now();
     CKI(ensure_shadow(ix, st));  // 2 = no memory for the shadow: the caller uses the scan path
+    cudaEvent_t* ev = ix->g_ev;
+    for (int i = 0; i < 5; ++i)
+        if (!ev[i]) CK(cudaEventCreate(&ev[i]));
+    CK(cudaEventRecord(ev[4], st));
     // ---- scratch ----
     const size_t qb_elems = (size_t)((m_tiles + 1) / 2 * 2) * G3_BLOCK_M * kpad;  // whole 256-query groups
     // sampled tiles: each contributes 8 group maxima; at most 8192 maxima per query are sorted
-    const uint32_t T = (uint32_t)std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(ix->opt_gemm_sample_tiles, 64), 1024), NT);
+    // expected emissions per query = emit_factor * k over ALL shards; a retry of uncertified queries (depth 1)
+    // widens the net 3x
+    double want = (double)std::max<int64_t>(ix->opt_gemm_emit_factor, 2) * (depth ? 3.0 : 1.0) * (double)k;
+    want = std::min(want, 0.7 * cap);
+    if (world > 1) want = std::max(want / world, 16.0);
+    uint32_t T = (uint32_t)std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(ix->opt_gemm_sample_tiles, 64), 1024), NT);
+    if (world > 1) {
+        // a shard samples only as many tiles as keep the selected rank near 10 (the rank is want * sampled / n)
+        const double t_need = 10.5 * (double)n / (want * G3_BLOCK_N);
+        T = (uint32_t)std::min<double>(T, std::max(64.0, std::ceil(t_need)));
+    }
     const uint32_t stride = std::max<uint32_t>(1, NT / T);
     if (ix->g_qb_cap < qb_elems || ix->g_q_cap < (size_t)nq || ix->g_tilemax_cap < (size_t)nq * T * 8 ||
         ix->g_cand_cap < (size_t)nq * cap)
@@ -1613,11 +1646,16 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     CKI(make_tmap_bf16(&tm_db, ix->sh_rows, n, (uint32_t)kpad, G3_BLOCK_N / cg));
     const bool masked = ix->cur_mask != nullptr;
     typedef void (*GemmFn)(const CUtensorMap, const CUtensorMap, const GemmParams);
-    GemmFn gfn = cg == 1 ? (masked ? gemm_topk_kernel<1, true> : gemm_topk_kernel<1, false>)
-                         : (masked ? gemm_topk_kernel<2, true> : gemm_topk_kernel<2, false>);
+    // [mode]: the tile-maxima pass and the emit pass are separate instantiations (no mode branches in the epilogue)
+    GemmFn gfns[2] = {
+        cg == 1 ? (masked ? gemm_topk_kernel<1, true, G3_MODE_TILEMAX> : gemm_topk_kernel<1, false, G3_MODE_TILEMAX>)
+                : (masked ? gemm_topk_kernel<2, true, G3_MODE_TILEMAX> : gemm_topk_kernel<2, false, G3_MODE_TILEMAX>),
+        cg == 1 ? (masked ? gemm_topk_kernel<1, true, G3_MODE_EMIT> : gemm_topk_kernel<1, false, G3_MODE_EMIT>)
+                : (masked ? gemm_topk_kernel<2, true, G3_MODE_EMIT> : gemm_topk_kernel<2, false, G3_MODE_EMIT>)};
     const size_t gsmem = cg == 1 ? G3Cfg<1>::kSmemBytes : G3Cfg<2>::kSmemBytes;
-    CK(cudaFuncSetAttribute(gfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    for (GemmFn f : gfns) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
     auto launch_gemm = [&](const GemmParams& g) -> int {
+        GemmFn gfn = gfns[g.mode == G3_MODE_EMIT ? 1 : 0];
         if (cg == 1) {
             gfn<<<ix->num_sms, G3_THREADS, gsmem, st>>>(tm_q, tm_db, g);
         } else {
@@ -1640,9 +1678,6 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
         CK(cudaGetLastError());
         return 0;
     };
-    cudaEvent_t* ev = ix->g_ev;
-    for (int i = 0; i < 4; ++i)
-        if (!ev[i]) CK(cudaEventCreate(&ev[i]));
     GemmParams gp;
     memset(&gp, 0, sizeof gp);
     gp.nq = (uint32_t)nq;
@@ -1679,9 +1714,6 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
         // is kept below G/8 so that two of the top scores rarely share a group.
         const uint32_t G = T * 8;
         double sample_rows = (double)T * G3_BLOCK_N;
-        // a retry of uncertified queries (depth 1) widens the net 3x
-        double want = (double)std::max<int64_t>(ix->opt_gemm_emit_factor, 2) * (depth ? 3.0 : 1.0) * (double)k;
-        want = std::min(want, 0.7 * cap);
         double r = want * std::min(1.0, sample_rows / (double)n);
         uint32_t rank = (uint32_t)std::min<double>(std::max(r, 8.0), (double)(G / 8));
         select_theta_kernel<<<(unsigned)nq, 256, 0, st>>>(ix->g_tilemax, G, rank, ix->g_theta);
@@ -1722,6 +1754,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     rp.D = D_dev;
     rp.I = I_dev;
     rp.certified = ix->g_cert;
+    rp.bound = bound_out;
     const size_t rsmem = (size_t)rp.qstride * 4 + (size_t)cap * 8;
     CK(cudaFuncSetAttribute(rerank_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
     CK(cudaFuncSetAttribute(rerank_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
@@ -1732,6 +1765,13 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     ++ix->launches;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev[3], st));
+    if (bound_out) {  // row-sharded form: nothing is read back here
+        ix->stat_gemm_used = 1;
+        ix->stat_gemm_fallbacks = -1;
+        ix->stat_gemm_cand_total = -1;
+        ix->g_ev_pending = true;
+        return 0;
+    }
     // ---- uncertified queries go through the exact scan ----
     std::vector<int> cert((size_t)nq);
     std::vector<unsigned int> counts((size_t)nq);
@@ -1739,9 +1779,14 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     CK(cudaMemcpyAsync(counts.data(), ix->g_count, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0;
+    ix->g_ev_pending = false;
     CK(cudaEventElapsedTime(&ms, ev[0], ev[1])); ix->stat_gemm_pass1_us = (int64_t)(ms * 1e3);
     CK(cudaEventElapsedTime(&ms, ev[1], ev[2])); ix->stat_gemm_pass2_us = (int64_t)(ms * 1e3);
     CK(cudaEventElapsedTime(&ms, ev[2], ev[3])); ix->stat_gemm_rerank_us = (int64_t)(ms * 1e3);
+    if (depth == 0) {
+        CK(cudaEventElapsedTime(&ms, ev[4], ev[0])); ix->stat_gemm_pre_us = (int64_t)(ms * 1e3);
+        ix->stat_gemm_host_us = (int64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - host_t0).count();
+    }
     std::vector<int64_t> bad;
     int64_t cand_total = 0;
     for (int64_t i = 0; i < nq; ++i) {
@@ -2255,6 +2300,85 @@ extern "C" int b200_normalize_rows(float* x_host, int64_t n, int d, int device) 
     cudaFree(dst);
     if (e != cudaSuccess) return fail("normalize_rows: %s", cudaGetErrorString(e));
     return rc;
+}
+
+// Row-sharded batch, local half (sharded.py): this index is one of `world` row shards.  Leaves in D/I the exact
+// fp32 scores of this shard's best candidates (best-first, padded) and in bound_dev[nq] the score no row outside
+// the list can beat; everything is enqueued on `stream`, nothing is read back.  Shards where the tensor-core path
+// does not apply (few rows, k > 256, no room for the shadow, a filter) answer with their exact top k from the scan
+// kernel and a bound that excludes nothing.  widen != 0 = second attempt for queries the merged certificate
+// rejected (3x more candidates).
+extern "C" int b200_index_search_shard_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, int world, int widen,
+                                           float* D_dev, int64_t* I_dev, float* bound_dev, void* stream) {
+    if (!ix) return fail("null index");
+    if (nq < 0) return fail("negative nq");
+    if (k <= 0) return fail("k must be positive, got %lld", (long long)k);
+    if (world < 1) return fail("world must be >= 1");
+    if (nq == 0) return 0;
+    if (!q_dev || !D_dev || !I_dev || !bound_dev) return fail("null buffer");
+    CKI(use_device(ix));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    const bool fullrank = k >= ix->opt_fullrank_min_k || k > B200_FUSED_K_MAX;
+    // at least 2 queries' worth of tensor work even when gemm_min_nq is lower; the caller decides what a batch is
+    const bool use_gemm = !fullrank && !ix->xchg_active && ix->ntotal > 0 && gemm_eligible(ix, std::max<int64_t>(nq, ix->opt_gemm_min_nq), k) &&
+                          ix->sh_failed_rows != ix->ntotal && ix->cur_mask == nullptr;
+    if (use_gemm) {
+        CKI(order_after_previous_stream(ix, st));
+        const float* q_raw = q_dev;
+        if (ix->opt_normalize_queries) {  // cosine: the bf16 query shadow is built from normalised queries (K1)
+            if (ix->qn_cap < (size_t)nq * ix->d) {
+                CK(cudaStreamSynchronize(st));
+                CKI(grow(&ix->qn_dev, &ix->qn_cap, (size_t)nq * ix->d));
+            }
+            CKI(ingest_dev(ix->d, ix->d, B200_STORE_F32, q_dev, (uint8_t*)ix->qn_dev, (size_t)ix->d * 4, nq, 1, ix->num_sms, st,
+                           &ix->launches));
+            q_dev = ix->qn_dev;
+        }
+        int rc = 0;
+        for (int64_t q0 = 0; q0 < nq && rc == 0; q0 += 16384) {
+            const int64_t nb = std::min<int64_t>(16384, nq - q0);
+            rc = search_gemm(ix, q_dev + (size_t)q0 * ix->d, nb, k, D_dev + (size_t)q0 * k, I_dev + (size_t)q0 * k, st,
+                             widen ? 1 : 0, bound_dev + q0, world);
+            if (rc == 2 && q0 != 0) return fail("the bf16 shadow disappeared between two blocks of one batch");
+        }
+        if (rc != 2) return rc;
+        q_dev = q_raw;
+    }
+    // exact local answer + neutral bound
+    const unsigned blocks = (unsigned)((nq + 255) / 256);
+    if (ix->metric == B200_METRIC_IP) fill_neutral_bound_kernel<0><<<blocks, 256, 0, st>>>(bound_dev, nq);
+    else fill_neutral_bound_kernel<1><<<blocks, 256, 0, st>>>(bound_dev, nq);
+    CK(cudaGetLastError());
+    const int64_t keep_min = ix->opt_gemm_min_nq;
+    ix->opt_gemm_min_nq = 0;  // the exact paths only (scan / full ranking)
+    int rc = b200_index_search_dev(ix, q_dev, nq, k, D_dev, I_dev, stream);
+    ix->opt_gemm_min_nq = keep_min;
+    return rc;
+}
+
+// K4 + certificate of a row-sharded batch: merges the G shard lists like b200_merge_topk_dev, then marks the queries
+// whose merged k-th entry does not strictly beat every shard's bound (bounds_parts_dev: shard g's bounds at
+// bounds_parts_dev + g * bound_part_stride floats).  n_total = rows in all shards.  uncertified_dev[nq] gets 0/1,
+// *n_uncertified_dev the count (zeroed here).
+extern "C" int b200_merge_certify_dev(int metric, int G, int64_t nq, int64_t k, int64_t n_total, const float* D_parts_dev,
+                                      const int64_t* I_parts_dev, int64_t D_part_stride, int64_t I_part_stride,
+                                      const float* bounds_parts_dev, int64_t bound_part_stride, float* D_out_dev,
+                                      int64_t* I_out_dev, int* uncertified_dev, int* n_uncertified_dev, void* stream) {
+    if (!bounds_parts_dev || !uncertified_dev || !n_uncertified_dev) return fail("null buffer");
+    if (n_total < 0) return fail("negative n_total");
+    int rc = b200_merge_topk_dev(metric, G, nq, k, D_parts_dev, I_parts_dev, D_part_stride, I_part_stride, D_out_dev, I_out_dev, stream);
+    if (rc || nq == 0) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(n_uncertified_dev, 0, sizeof(int), st));
+    const int64_t want = std::min<int64_t>(k, n_total);
+    const int64_t bs = bound_part_stride ? bound_part_stride : nq;
+    const unsigned blocks = (unsigned)((nq + 255) / 256);
+    if (metric == B200_METRIC_IP)
+        merge_certify_kernel<0><<<blocks, 256, 0, st>>>(G, nq, k, want, D_out_dev, bounds_parts_dev, bs, uncertified_dev, n_uncertified_dev);
+    else
+        merge_certify_kernel<1><<<blocks, 256, 0, st>>>(G, nq, k, want, D_out_dev, bounds_parts_dev, bs, uncertified_dev, n_uncertified_dev);
+    CK(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int b200_merge_topk_dev(int metric, int G, int64_t nq, int64_t k, const float* D_parts_dev,

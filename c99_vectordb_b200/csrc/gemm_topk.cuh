@@ -89,6 +89,33 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[3
         : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same wait, tied to the registers of the load it completes: nothing that reads v[] can be scheduled above
+// it (a second tcgen05.ld may stay in flight across this point — the epilogue's software pipeline)
+__device__ __forceinline__ void tc_wait_ld_for(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+// maximum of 32 accumulator columns as a balanced tree (the compiler pairs the levels into 3-input FMNMX3)
+__device__ __forceinline__ float g3_max32(const uint32_t (&v)[32]) {
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        m[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
+                     fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+    return fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+}
+// the same with the columns whose bit in `ok` is clear left out (ragged last tile, filtered search)
+__device__ __forceinline__ float g3_max32_where(const uint32_t (&v)[32], uint32_t ok) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) m = fmaxf(m, ((ok >> j) & 1u) ? __uint_as_float(v[j]) : -INFINITY);
+    return m;
+}
 
 // K-major operand tile in shared memory written by TMA with CU_TENSOR_MAP_SWIZZLE_128B:
 // rows of 128 bytes, 8-row groups 1024 bytes apart.  Descriptor fields (cute::UMMA::SmemDescriptor):
@@ -192,7 +219,7 @@ struct G3Cfg {
 // cores share the row operand, which halves shared-memory traffic per SM (the cta_group::1 form is
 // capped near 2/3 of peak by the 128 B/cycle smem port: 96 B/cycle of operand reads + 96 B/cycle of
 // TMA fills).  Only the pair's leader (rank 0) issues MMAs; both CTAs run TMA and the epilogue.
-template <int CG, bool MASKED>
+template <int CG, bool MASKED, int MODE>
 __global__ void __launch_bounds__(G3_THREADS, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
                  const GemmParams p) {
@@ -329,7 +356,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             const uint32_t qidx = mt * G3_BLOCK_M + quarter * 32u + (uint32_t)lane;
             const bool qlive = qidx < p.nq;
             float theta = INFINITY;
-            if (p.mode == G3_MODE_EMIT && qlive) theta = p.theta[qidx];
+            if (MODE == G3_MODE_EMIT && qlive) theta = p.theta[qidx];
             for (uint32_t t = t0; t < t1; ++t) {
                 const uint32_t ntile = p.tile_first + t * p.tile_stride;
                 const uint64_t row0 = (uint64_t)ntile * G3_BLOCK_N;
@@ -338,33 +365,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 tc_fence_after();
                 const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + abuf * G3_BLOCK_N;
                 float gmax[G3_BLOCK_N / 32];
-#pragma unroll
-                for (uint32_t c0 = 0; c0 < G3_BLOCK_N; c0 += 32) {
-                    uint32_t v[32];
-                    tc_ld_32x32b_x32(taddr0 + c0, v);
-                    tc_wait_ld();
-                    gmax[c0 / 32] = -INFINITY;
-                    if (c0 >= live_cols) continue;  // rows past the end of the database (zero filled by TMA)
-                    // MASKED: one aligned mask word covers these 32 rows (tiles start at multiples of 256)
-                    uint32_t mw = 0xFFFFFFFFu;
-                    if (MASKED) mw = __ldg(p.row_mask + ((row0 + c0) >> 5));
-                    float m = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float s = __uint_as_float(v[j]);
-                        if (c0 + j >= live_cols) s = -INFINITY;
-                        if (MASKED && !((mw >> j) & 1u)) s = -INFINITY;
-                        m = fmaxf(m, s);
-                    }
-                    gmax[c0 / 32] = m;
-                    if (p.mode == G3_MODE_EMIT && m > theta) {
-                        // rare (this thread's query has a candidate among these 32 rows): build the
-                        // hit mask in registers, then append the rows
+                // one 32-column group: its maximum, and (EMIT) the rare append of the rows above theta.
+                // `ok` (live columns of a ragged last tile & the filter's mask word) is the same for every
+                // thread of the warp, so the all-ones test is a uniform branch and the common case is 16
+                // FMNMX3 + one compare per 32 scores.
+                auto group = [&](const uint32_t (&v)[32], uint32_t g) {
+                    const uint32_t c0 = g * 32u;
+                    uint32_t ok = c0 >= live_cols ? 0u : (live_cols - c0 >= 32u ? 0xFFFFFFFFu : (1u << (live_cols - c0)) - 1u);
+                    if (MASKED && ok) ok &= __ldg(p.row_mask + ((row0 + c0) >> 5));  // tiles start at multiples of 256 rows
+                    float m;
+                    if (ok == 0xFFFFFFFFu) m = g3_max32(v);
+                    else if (ok == 0u) m = -INFINITY;  // rows past the end of the database (zero filled by TMA)
+                    else m = g3_max32_where(v, ok);
+                    if (MODE == G3_MODE_TILEMAX) gmax[g] = m;
+                    if (MODE == G3_MODE_EMIT && m > theta) {
                         uint32_t hit = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            hit |= (__uint_as_float(v[j]) > theta && c0 + j < live_cols) ? (1u << j) : 0u;
-                        if (MASKED) hit &= mw;
+                        for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(v[j]) > theta) ? (1u << j) : 0u;
+                        hit &= ok;
                         while (hit) {
                             const int j = __ffs(hit) - 1;
                             hit &= hit - 1;
@@ -372,17 +390,34 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                             if (pos < p.cand_cap) p.cand_rows[(size_t)qidx * p.cand_cap + pos] = (uint32_t)(row0 + c0 + j);
                         }
                     }
+                };
+                // software pipeline over the 8 column groups: the tcgen05.ld of group g+1 is in flight while
+                // group g is reduced; the accumulator is handed back to the MMA warp as soon as the last
+                // load has landed, before the last group is processed
+                uint32_t va[32], vb[32];
+                tc_ld_32x32b_x32(taddr0, va);
+#pragma unroll
+                for (uint32_t g = 0; g < G3_BLOCK_N / 32; g += 2) {
+                    tc_wait_ld_for(va);
+                    tc_ld_32x32b_x32(taddr0 + (g + 1) * 32u, vb);
+                    group(va, g);
+                    tc_wait_ld_for(vb);
+                    if (g + 2 < G3_BLOCK_N / 32) {
+                        tc_ld_32x32b_x32(taddr0 + (g + 2) * 32u, va);
+                    } else {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 1) mbar_arrive(tempty_bar(abuf));
+                            else mbar_arrive_cluster(tempty_lead0 + 8u * abuf);  // the leader's MMA warp waits for both CTAs
+                        }
+                    }
+                    group(vb, g + 1);
                 }
-                if (p.mode == G3_MODE_TILEMAX && qlive) {
+                if (MODE == G3_MODE_TILEMAX && qlive) {
                     float4* dst = reinterpret_cast<float4*>(p.tilemax + ((size_t)qidx * p.tile_count + t) * 8);
                     dst[0] = make_float4(gmax[0], gmax[1], gmax[2], gmax[3]);
                     dst[1] = make_float4(gmax[4], gmax[5], gmax[6], gmax[7]);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 1) mbar_arrive(tempty_bar(abuf));
-                    else mbar_arrive_cluster(tempty_lead0 + 8u * abuf);  // the leader's MMA warp waits for both CTAs
                 }
                 if (++abuf == 2) {
                     abuf = 0;
@@ -508,6 +543,7 @@ struct RerankParams {
     float* D;
     int64_t* I;
     int* certified;        // [nq] 1 = result proven exact, 0 = must be recomputed by the exact scan
+    float* bound;          // optional [nq] (row-sharded batches): no row outside the list scores better than this
 };
 
 template <int METRIC>
@@ -612,5 +648,23 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
             }
         }
         p.certified[qi] = ok ? 1 : 0;
+        if (p.bound) {
+            // Row-sharded batch: the certificate is taken after the merge, over all shards.  A row of this shard
+            // that is not in the list was either not emitted — exact score no better than theta + eps (IP) /
+            // |q|^2 - 2 (theta + eps_a) - slack (L2) — or cut off behind k better entries of this very list.
+            // An overflowed candidate list proves nothing: the bound says so.
+            const float maxn = sqrtf(__uint_as_float(*p.max_norm2_bits));
+            const float qn2 = p.qnorm2[qi], qn = sqrtf(qn2);
+            const float eps = p.eps_rel * qn * maxn;
+            float b;
+            if (METRIC == 0) {
+                b = count <= p.cand_cap ? p.theta[qi] + eps : INFINITY;
+            } else {
+                const float eps_a = eps + 2e-5f * maxn * maxn;
+                const float slack = 4.0f * (float)p.d * 6e-8f * (qn + maxn) * (qn + maxn);
+                b = count <= p.cand_cap ? qn2 - 2.0f * (p.theta[qi] + eps_a) - slack : -INFINITY;
+            }
+            p.bound[qi] = b;
+        }
     }
 }

@@ -62,3 +62,33 @@ merge_topk_kernel(int G, int64_t nq, int64_t k, const float* __restrict__ Dp,
         }
     }
 }
+
+// Certificate of a merged row-sharded batch (K3 per shard, cabi.cu b200_index_search_shard_dev): query q is proven
+// exact iff its merged k-th entry (k = min(k, rows in all shards)) exists and strictly beats every shard's bound —
+// nothing outside the shards' lists can then belong to the top k.  uncertified[q] = 1 and *n_uncertified counts the rest.
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+merge_certify_kernel(int G, int64_t nq, int64_t k, int64_t want, const float* __restrict__ Do,
+                     const float* __restrict__ bounds, int64_t bstride, int* __restrict__ uncertified,
+                     int* __restrict__ n_uncertified) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    bool ok = true;
+    if (want > 0) {
+        const float kth = Do[q * k + want - 1];
+        ok = b200_score_valid<METRIC>(kth);
+        for (int g = 0; g < G && ok; ++g) {
+            const float b = bounds[(int64_t)g * bstride + q];
+            ok = METRIC == 0 ? (kth > b) : (kth < b);
+        }
+    }
+    uncertified[q] = ok ? 0 : 1;
+    if (!ok) atomicAdd(n_uncertified, 1);
+}
+
+// bound that excludes nothing: the list it travels with is this shard's exact top k
+template <int METRIC>
+__global__ void fill_neutral_bound_kernel(float* bound, int64_t nq) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) bound[q] = METRIC == 0 ? -INFINITY : INFINITY;
+}

@@ -232,6 +232,23 @@ int b200_normalize_rows(float* x_host, int64_t n, int d, int device);
 int b200_merge_topk_dev(int metric, int G, int64_t nq, int64_t k, const float* D_parts_dev,
                         const int64_t* I_parts_dev, int64_t D_part_stride, int64_t I_part_stride,
                         float* D_out_dev, int64_t* I_out_dev, void* stream);
+/* Row-sharded batches on the tensor-core path (sharded.py; no analogue in memo_cli.py, which is one process):
+ * b200_index_search_shard_dev is the local half on one of `world` row shards — D/I receive the exact fp32 scores
+ * of this shard's best candidates (best-first, padded like b200_index_search) and bound_dev[nq] the score that no
+ * row outside the list can beat; thresholds aim at 1/world of the candidates a single index would collect, so the
+ * exact re-rank shrinks with the shard.  Everything is enqueued on `stream`; nothing is read back.  Shards the
+ * tensor-core path does not serve (few rows, k > 256, no room for the bf16 shadow) answer with their exact top k
+ * and a bound that excludes nothing.  widen != 0: second attempt with 3x more candidates.
+ * b200_merge_certify_dev merges the gathered shard lists (as b200_merge_topk_dev) and takes the certificate over
+ * all shards: uncertified_dev[q] = 1 unless the merged k-th entry (k clipped to n_total) strictly beats every
+ * shard's bound; *n_uncertified_dev counts them.  Uncertified queries are searched again by the caller (widened,
+ * then with the exact scan), so results stay exact. */
+int b200_index_search_shard_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, int world, int widen,
+                                float* D_dev, int64_t* I_dev, float* bound_dev, void* stream);
+int b200_merge_certify_dev(int metric, int G, int64_t nq, int64_t k, int64_t n_total, const float* D_parts_dev,
+                           const int64_t* I_parts_dev, int64_t D_part_stride, int64_t I_part_stride,
+                           const float* bounds_parts_dev, int64_t bound_part_stride, float* D_out_dev,
+                           int64_t* I_out_dev, int* uncertified_dev, int* n_uncertified_dev, void* stream);
 /* Host-side bulk hashing-trick embedder (replaces the token loop of embed_text_hash,
  * memo_cli.py:158-166) with CPython's str hash fixed to the PYTHONHASHSEED=0 key: n lower-cased
  * UTF-8 texts concatenated in utf8, text i = [offsets[i], offsets[i+1]); out is [n,dim] float32

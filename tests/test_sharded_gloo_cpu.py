@@ -35,6 +35,84 @@ class OracleLocalIndex:
         return oracle.search(self.metric, self.rows, q, k, ids=self.ids)
 
 
+class ApproxLocalIndex(OracleLocalIndex):
+    """The row-sharded batch protocol of b200_index_search_shard_dev restated on the CPU: an approximate pass
+    (exact score + bounded noise, standing in for the bf16 GEMM) emits the rows above a threshold that aims at
+    c*k/world candidates, the candidates are re-ranked exactly, and the shard reports the bound no other row of it can
+    beat.  Small candidate budgets make some certificates fail, which exercises the widened retry and the exact
+    fallback."""
+
+    EPS = 0.02
+
+    def __init__(self, d, metric):
+        super().__init__(d, metric)
+        self.calls = []
+
+    def search_shard(self, q, k, world, widen):
+        self.calls.append((q.shape[0], widen))
+        nq, n = q.shape[0], self.rows.shape[0]
+        big = np.finfo(np.float32).max
+        D = np.full((nq, k), -big if self.metric == 0 else big, np.float32)
+        I = np.full((nq, k), -1, np.int64)
+        B = np.full(nq, -np.inf if self.metric == 0 else np.inf, np.float32)
+        if n == 0:
+            return D, I, B
+        rng = np.random.default_rng(1234 + n + widen)
+        for i in range(nq):
+            exact = (self.rows @ q[i]) if self.metric == 0 else ((self.rows - q[i]) ** 2).sum(axis=1)
+            approx = exact + rng.uniform(-self.EPS, self.EPS, size=n).astype(np.float32)
+            want = min(n, max(2, int((6 if widen else 1.2) * k / world)))
+            order = np.sort(approx)
+            if self.metric == 0:
+                theta = order[n - want] - 1e-6 if want < n else -np.inf
+                cand = np.nonzero(approx > theta)[0]
+                B[i] = theta + self.EPS
+            else:
+                theta = order[want - 1] + 1e-6 if want < n else np.inf
+                cand = np.nonzero(approx < theta)[0]
+                B[i] = theta - self.EPS
+            Dc, Ic = oracle.search(self.metric, self.rows[cand], q[i:i + 1], k, ids=self.ids[cand])
+            D[i], I[i] = Dc[0], Ic[0]
+        return D, I, B
+
+
+def _batch_worker(rank, world, port, metric, n, d, k, nq, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        base = oracle.synth_rows(n // 2, d, 9)
+        db = np.concatenate([base, base, oracle.synth_rows(n - 2 * (n // 2), d, 10)])  # cross-shard exact ties
+        ids = np.arange(n, dtype=np.int64) * 7 + 3
+        q = oracle.synth_rows(nq, d, 8)
+        local = ApproxLocalIndex(d, metric)
+        idx = ShardedIndexFlat(d, metric, local_index=local, merge_fn=oracle.merge_topk, device="cpu")
+        idx.add_with_ids(db, ids)
+        D, I = idx.search(q, k)
+        Dw, Iw = oracle.search(metric, db, q, k, ids=ids)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)
+        np.save(os.path.join(out_dir, f"calls_{rank}.npy"), np.asarray(local.calls, dtype=np.int64))
+        np.save(os.path.join(out_dir, f"unc_{rank}.npy"), np.asarray([idx.last_batch_uncertified]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,metric,n,k,nq", [(2, 0, 4001, 10, 24), (3, 1, 3000, 5, 16), (2, 1, 7, 5, 4)])
+def test_sharded_batch_certificate_after_merge(tmp_path, world, metric, n, k, nq):
+    """Batches: approximate candidates per shard, certificate over all shards after the merge, widened retry, exact
+    fallback — the answer equals the unsharded oracle whatever the approximate pass did."""
+    mp.spawn(_batch_worker, args=(world, _free_port(), metric, n, 24, k, nq, str(tmp_path)), nprocs=world, join=True)
+    calls = [np.load(tmp_path / f"calls_{r}.npy") for r in range(world)]
+    for c in calls[1:]:
+        np.testing.assert_array_equal(c, calls[0])  # every rank took the same decisions
+    assert calls[0][0].tolist() == [nq, 0]
+    unc = int(np.load(tmp_path / "unc_0.npy")[0])
+    if n > 1000:
+        assert 0 < unc, "the small candidate budget was meant to leave some queries uncertified"
+        assert len(calls[0]) >= 2 and calls[0][1].tolist() == [unc, 1]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -82,6 +82,19 @@ def _worker(rank, world, port, out_dir):
         Dw2, Iw2 = oracle.search(1, oracle.synth_rows(300_000, 384, 1234), qb, 10, order=oracle.ORDER_DEVICE)
         np.testing.assert_array_equal(Ib, Iw2)
         np.testing.assert_array_equal(Db, Dw2)
+        # starved thresholds: the certificate taken after the merge rejects queries, the widened retry and the exact
+        # scan finish them — the answer stays exact and every rank takes the same decisions
+        idx.local.index.set_option("gemm_min_nq", 2)
+        idx.local.index.set_option("gemm_min_rows", 4096)
+        idx.local.index.set_option("gemm_emit_factor", 2)
+        qs = oracle.synth_rows(48, 384, 777)
+        Ds, Is = idx.search(qs, 40)
+        Dw3, Iw3 = oracle.search(1, oracle.synth_rows(300_000, 384, 1234), qs, 40, order=oracle.ORDER_DEVICE)
+        np.testing.assert_array_equal(Is, Iw3)
+        np.testing.assert_array_equal(Ds, Dw3)
+        if idx.local.index.get_option("stat_gemm_used") == 1:
+            assert idx.last_batch_uncertified is not None and idx.last_batch_uncertified > 0
+        idx.local.index.set_option("gemm_emit_factor", 8)
         q1 = oracle.synth_rows(1, 384, 31337)
         Dw1, Iw1 = oracle.search(1, oracle.synth_rows(300_000, 384, 1234), q1, 10, order=oracle.ORDER_DEVICE)
         for rep in range(20):  # back-to-back fused searches exercise the double-buffered slots
