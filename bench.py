@@ -631,15 +631,16 @@ def run_workload(env: Env, a, workload: str, steps: int, warmup: int, *, headlin
         ref.local.index.close()
     if gemm_used and line is not None:
         # batched path: the dominant kernel is the tcgen05 emit pass; algorithmic flops = 2 nq N d
-        p2_ms = base.get_option("stat_gemm_pass2_us") / 1e3
+        gstat = (lambda name: base.get_option("stat_gemm_" + name)) if world == 1 or not idx.last_batch_stats else (lambda name: idx.last_batch_stats[name])
+        p2_ms = gstat("pass2_us") / 1e3
         flops = 2.0 * nq * (hi - lo) * d
         tpeak, tsrc = measured_tensor_peak()
         line["roofline"] = {"bound": "tensor", "achieved": flops / (p2_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                             "frac": flops / (p2_ms * 1e-3) / 1e12 / tpeak, "traffic": None, "kernel": "gemm_topk_kernel (emit pass)",
                             "flops_per_launch": flops, "avg_launch_ms": p2_ms, "peak_source": tsrc,
                             "whole_step_tflops": 2.0 * nq * n * d / (total_ms / steps * 1e-3) / 1e12,
-                            "pass1_ms": base.get_option("stat_gemm_pass1_us") / 1e3,
-                            "rerank_ms": base.get_option("stat_gemm_rerank_us") / 1e3,
+                            "pass1_ms": gstat("pass1_us") / 1e3,
+                            "rerank_ms": gstat("rerank_us") / 1e3,
                             "uncertified_queries_recomputed": (base.get_option("stat_gemm_fallbacks") if world == 1
                                                                else idx.last_batch_uncertified),
                             "candidates_per_query": (base.get_option("stat_gemm_cand_total") / nq if world == 1 else None),

@@ -1610,7 +1610,9 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     // widens the net 3x
     double want = (double)std::max<int64_t>(ix->opt_gemm_emit_factor, 2) * (depth ? 3.0 : 1.0) * (double)k;
     want = std::min(want, 0.7 * cap);
-    if (world > 1) want = std::max(want / world, 16.0);
+    // (a shard aims 30% above its share: the merged certificate has to beat the HIGHEST of the shards' thresholds,
+    // which independent estimates push up)
+    if (world > 1) want = std::max(1.3 * want / world, 16.0);
     uint32_t T = (uint32_t)std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(ix->opt_gemm_sample_tiles, 64), 1024), NT);
     if (world > 1) {
         // a shard samples only as many tiles as keep the selected rank near 10 (the rank is want * sampled / n)

@@ -69,6 +69,7 @@ class ShardedIndexFlat:
         self._fused = False
         self._host_stage = {}
         self.last_batch_uncertified = None
+        self.last_batch_stats = None
 
     # ---- add --------------------------------------------------------------------------------
     def add_with_ids(self, x: np.ndarray, ids: np.ndarray) -> None:
@@ -284,6 +285,9 @@ class ShardedIndexFlat:
         bad_count = int(n_unc.item())  # one 4-byte read per batch: every rank sees the same count
         if widen == 0:
             self.last_batch_uncertified = bad_count  # of this batch's first attempt (bench.py reports it)
+            if cuda:  # the pass brackets of the first attempt, before a retry overwrites them
+                base = self.local.index
+                self.last_batch_stats = {s: base.get_option("stat_gemm_" + s) for s in ("used", "pass1_us", "pass2_us", "rerank_us")}
         if bad_count:
             bad = torch.nonzero(unc, as_tuple=False).flatten()
             q_bad = q.index_select(0, bad).contiguous()

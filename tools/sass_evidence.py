@@ -9,7 +9,7 @@ ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "c99_vectordb_b200" / "_b200flat.so"
 FAMILIES = [("UTCHMMA", "tcgen05.mma kind::f16"), ("UTCBAR", "tcgen05.commit"), ("LDTM", "tcgen05.ld"), ("UTCATOMSWS", "tcgen05.alloc"),
             ("UTMALDG", "cp.async.bulk.tensor (TMA tile load)"), ("UBLKCP", "cp.async.bulk (TMA bulk copy)"),
-            ("UTMAPF", "prefetch.tensormap"), ("SYNCS", "mbarrier"), ("ACQBULK", "griddepcontrol / bulk acquire"),
+            ("UTMAPF", "prefetch.tensormap"), ("SYNCS", "mbarrier"), ("ACQBULK", "griddepcontrol.wait"), ("PREEXIT", "griddepcontrol.launch_dependents"),
             ("FMNMX3", "3-input max"), ("UCGABAR", "barrier.cluster")]
 
 
