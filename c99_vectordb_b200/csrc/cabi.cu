@@ -110,11 +110,12 @@ struct b200_index {
             opt_normalize_queries = 0, opt_staged_results = 1, opt_qb = 0, opt_dynamic = -1, opt_claim_chunk = 0, opt_fused_tail = -1,
             opt_claim_min = 0, opt_claim_first = 0, opt_pdl = 1, opt_queries_stable = 0, opt_phase_stamps = 0, opt_fuse_query_norm = 1;
     bool cur_norm_q = false;  // the scan launches of the search in flight normalise their queries themselves
-    int64_t opt_gemm_min_rows = 4096, opt_gemm_min_nq = 2, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2;
+    int64_t opt_gemm_min_rows = 4096, opt_gemm_min_nq = 2, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2,
+            opt_gemm_shadow_max_rows = 0;  // > 0: keep at most this many rows of the bf16 shadow resident (streamed beyond; tests)
     // read-only statistics of the last batched (K3) search
     int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
             stat_gemm_pass2_us = 0, stat_gemm_rerank_us = 0, stat_gemm_scan_fallbacks = 0, stat_gemm_pre_us = 0,
-            stat_gemm_host_us = 0;
+            stat_gemm_host_us = 0, stat_gemm_streamed = 0;
     // K3 state
     __nv_bfloat16* sh_rows = nullptr;  // bf16 shadow of the rows [ntotal, kpad]
     float* sh_norm2 = nullptr;
@@ -122,6 +123,9 @@ struct b200_index {
     int64_t sh_valid_rows = -1;        // rows covered by the shadow (-1 = none)
     int64_t sh_failed_rows = -1;       // ntotal at which the shadow allocation last failed (no retry until it changes)
     size_t sh_cap_rows = 0;
+    bool sh_streamed = false;          // the shadow does not fit: sh_rows is a scratch of sh_cap_rows rows, refilled chunk by chunk per search
+    cudaStream_t sh_stream2 = nullptr; // streamed shadow: the converter of chunk c+1 runs here while the GEMM sweeps chunk c
+    cudaEvent_t sh_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0,1] chunk converted, [2,3] chunk swept, [4] fork
     __nv_bfloat16* g_qb = nullptr;     // bf16 queries [m_tiles*128, kpad]
     float* g_qnorm2 = nullptr;
     float* g_tilemax = nullptr;
@@ -292,6 +296,9 @@ extern "C" int b200_index_destroy(b200_index* ix) {
     cudaFree(ix->idbits_dev);
     cudaFree(ix->ids_minmax_dev);
     cudaFree(ix->sh_rows);
+    if (ix->sh_stream2) cudaStreamDestroy(ix->sh_stream2);
+    for (int i = 0; i < 5; ++i)
+        if (ix->sh_ev[i]) cudaEventDestroy(ix->sh_ev[i]);
     cudaFree(ix->sh_norm2);
     cudaFree(ix->sh_maxnorm);
     cudaFree(ix->g_qb);
@@ -390,6 +397,8 @@ static const OptName kOpts[] = {
     {"gemm_chunk_tiles", &b200_index::opt_gemm_chunk_tiles},
     {"gemm_sample_tiles", &b200_index::opt_gemm_sample_tiles},
     {"gemm_cta_group", &b200_index::opt_gemm_cta_group},
+    {"gemm_shadow_max_rows", &b200_index::opt_gemm_shadow_max_rows},
+    {"stat_gemm_streamed", &b200_index::stat_gemm_streamed},
     {"stat_gemm_used", &b200_index::stat_gemm_used},
     {"stat_gemm_fallbacks", &b200_index::stat_gemm_fallbacks},
     {"stat_gemm_scan_fallbacks", &b200_index::stat_gemm_scan_fallbacks},
@@ -1548,34 +1557,81 @@ static int gemm_kpad(const b200_index* ix) {
     return (cols + G3_BLOCK_K - 1) / G3_BLOCK_K * G3_BLOCK_K;
 }
 
+// Sampled tiles the threshold pass needs at least: theta is never taken above the 8th largest sampled group maximum,
+// so a query emits about 8 * n / sampled_rows candidates however few are wanted; keeping that under a quarter of the
+// candidate list (1024 of 4096) takes a sample that grows with the database (100M rows: 3052 tiles = 0.8 % of it).
+static uint32_t gemm_min_sample_tiles(int64_t n) {
+    const double t = std::ceil(8.0 * (double)n / (1024.0 * G3_BLOCK_N));
+    return (uint32_t)std::min(8192.0, std::max(1.0, t));
+}
+// queries per K3 call: bounds the candidate lists (16 KB per query) and the sampled maxima (32 B per query and tile)
+static int64_t gemm_query_block(const b200_index* ix) {
+    const uint32_t t = std::max<uint32_t>(1024, gemm_min_sample_tiles(ix->ntotal));
+    return std::max<int64_t>(1024, (int64_t)16384 * 1024 / t / 256 * 256);
+}
+
+// Rows of the streamed scratch (a multiple of 512: two chunk buffers of whole 256-row tiles): two chunks of ~256 MB
+// of bf16 each — large enough to amortise the two launches per chunk, and the converter of chunk c+1 overlaps the sweep
+// of chunk c — but at least the sampled tiles of the threshold pass, which are packed into the same scratch.
+static size_t shadow_stream_rows(const b200_index* ix, int kpad) {
+    size_t rows = 2 * (((size_t)256 << 20) / ((size_t)kpad * 2) / G3_BLOCK_N * G3_BLOCK_N);
+    rows = std::max<size_t>(rows, ((size_t)std::max<uint32_t>(1024, gemm_min_sample_tiles(ix->ntotal)) + 1) / 2 * 2 * G3_BLOCK_N);
+    if (ix->opt_gemm_shadow_max_rows > 0)
+        rows = std::max<size_t>(2 * G3_BLOCK_N, (size_t)ix->opt_gemm_shadow_max_rows / (2 * G3_BLOCK_N) * (2 * G3_BLOCK_N));
+    return rows;
+}
+
+// 0: the whole bf16 shadow is resident and current.  3: it does not fit next to the rows (or option
+// gemm_shadow_max_rows caps it): sh_rows is a scratch of sh_cap_rows rows and the search streams the rows through it
+// chunk by chunk.  2: not even the scratch could be allocated — the caller uses the scan path.
 static int ensure_shadow(b200_index* ix, cudaStream_t st) {
     const int kpad = gemm_kpad(ix);
-    if (ix->sh_valid_rows == ix->ntotal) return 0;
-    if (ix->sh_cap_rows < (size_t)ix->ntotal) {
+    if (!ix->sh_maxnorm) CK(cudaMalloc((void**)&ix->sh_maxnorm, sizeof(unsigned int)));
+    const bool capped = ix->opt_gemm_shadow_max_rows > 0 && ix->ntotal > ix->opt_gemm_shadow_max_rows;
+    if (!ix->sh_streamed && !capped && ix->sh_valid_rows == ix->ntotal) return 0;
+    if (ix->sh_streamed && ix->sh_valid_rows == ix->ntotal && ix->sh_cap_rows == shadow_stream_rows(ix, kpad)) return 3;
+    bool want_stream = capped;
+    if (!want_stream && (ix->sh_streamed || ix->sh_cap_rows < (size_t)ix->ntotal)) {
         CK(cudaStreamSynchronize(st));
         if (ix->sh_rows) CK(cudaFree(ix->sh_rows));
-        if (ix->sh_norm2) CK(cudaFree(ix->sh_norm2));
         ix->sh_rows = nullptr;
-        ix->sh_norm2 = nullptr;
         ix->sh_cap_rows = 0;
+        ix->sh_streamed = false;
         size_t cap = (size_t)ix->ntotal;  // the rows present, not the reserved capacity: the shadow is rebuilt on change anyway
         cudaError_t e = cudaMalloc((void**)&ix->sh_rows, cap * kpad * sizeof(__nv_bfloat16));
-        if (e == cudaSuccess) e = cudaMalloc((void**)&ix->sh_norm2, cap * sizeof(float));
         if (e != cudaSuccess) {
-            // not an error for the search: the caller falls back to the exact scan (status 2)
             cudaGetLastError();
-            if (ix->sh_rows) cudaFree(ix->sh_rows);
             ix->sh_rows = nullptr;
-            ix->sh_failed_rows = ix->ntotal;
-            fail("no room for the %.2f GB bf16 shadow: %s", (double)cap * kpad * 2 / 1e9, cudaGetErrorString(e));
-            return 2;
+            want_stream = true;  // no room for a resident copy: stream the rows through a scratch instead
+        } else {
+            ix->sh_cap_rows = cap;
         }
-        ix->sh_cap_rows = cap;
     }
-    if (!ix->sh_maxnorm) CK(cudaMalloc((void**)&ix->sh_maxnorm, sizeof(unsigned int)));
+    if (want_stream) {
+        const size_t rows = shadow_stream_rows(ix, kpad);
+        if (!ix->sh_streamed || ix->sh_cap_rows != rows) {
+            CK(cudaStreamSynchronize(st));
+            if (ix->sh_rows) CK(cudaFree(ix->sh_rows));
+            ix->sh_rows = nullptr;
+            ix->sh_cap_rows = 0;
+            ix->sh_streamed = false;
+            cudaError_t e = cudaMalloc((void**)&ix->sh_rows, rows * kpad * sizeof(__nv_bfloat16));
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                ix->sh_rows = nullptr;
+                ix->sh_failed_rows = ix->ntotal;
+                fail("no room for the %.2f GB bf16 scratch: %s", (double)rows * kpad * 2 / 1e9, cudaGetErrorString(e));
+                return 2;
+            }
+            ix->sh_cap_rows = rows;
+            ix->sh_streamed = true;
+        }
+        ix->sh_valid_rows = ix->ntotal;
+        return 3;
+    }
     CK(cudaMemsetAsync(ix->sh_maxnorm, 0, sizeof(unsigned int), st));
-    shadow_rows_kernel<<<ix->num_sms * 8, 256, 0, st>>>(ix->rows, ix->pitch, ix->store, (uint64_t)ix->ntotal, ix->d, kpad,
-                                                        ix->metric == B200_METRIC_L2 ? 1 : 0, ix->sh_rows, ix->sh_norm2,
+    shadow_rows_kernel<<<ix->num_sms * 4, 256, 0, st>>>(ix->rows, ix->pitch, ix->store, (uint64_t)ix->ntotal, (uint64_t)ix->ntotal, 1,
+                                                        ix->d, kpad, ix->metric == B200_METRIC_L2 ? 1 : 0, ix->sh_rows, nullptr,
                                                         ix->sh_maxnorm);
     ++ix->launches;
     CK(cudaGetLastError());
@@ -1598,7 +1654,10 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     const uint32_t cap = 4096;
     const int cg = ix->opt_gemm_cta_group == 1 ? 1 : 2;
     const auto host_t0 = std::chrono::steady_clock::now();
-    CKI(ensure_shadow(ix, st));  // 2 = no memory for the shadow: the caller uses the scan path
+    const int shadow_state = ensure_shadow(ix, st);  // 2 = not even a scratch: the caller uses the scan path
+    if (shadow_state != 0 && shadow_state != 3) return shadow_state;
+    const bool streamed = shadow_state == 3;
+    const size_t S = ix->sh_cap_rows;  // streamed: rows per chunk
     cudaEvent_t* ev = ix->g_ev;
     for (int i = 0; i < 5; ++i)
         if (!ev[i]) CK(cudaEventCreate(&ev[i]));
@@ -1614,6 +1673,8 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     // which independent estimates push up)
     if (world > 1) want = std::max(1.3 * want / world, 16.0);
     uint32_t T = (uint32_t)std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(ix->opt_gemm_sample_tiles, 64), 1024), NT);
+    T = std::min<uint32_t>(NT, std::max<uint32_t>(T, gemm_min_sample_tiles(ix->ntotal)));
+    if (streamed) T = (uint32_t)std::min<size_t>(T, S / G3_BLOCK_N);  // the sampled tiles are packed into the scratch
     if (world > 1) {
         // a shard samples only as many tiles as keep the selected rank near 10 (the rank is want * sampled / n)
         const double t_need = 10.5 * (double)n / (want * G3_BLOCK_N);
@@ -1639,13 +1700,18 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     // ---- query shadow (zero padded to whole 128-query tiles) ----
     CK(cudaMemsetAsync(ix->g_qb, 0, qb_elems * sizeof(__nv_bfloat16), st));
     shadow_rows_kernel<<<(unsigned)std::min<int64_t>((nq + 7) / 8, ix->num_sms * 8), 256, 0, st>>>(
-        (const uint8_t*)q_dev, (uint64_t)ix->d * 4, 0, (uint64_t)nq, ix->d, kpad, ix->metric == B200_METRIC_L2 ? 2 : 0,
+        (const uint8_t*)q_dev, (uint64_t)ix->d * 4, 0, (uint64_t)nq, (uint64_t)nq, 1, ix->d, kpad, ix->metric == B200_METRIC_L2 ? 2 : 0,
         ix->g_qb, ix->g_qnorm2, nullptr);
     ++ix->launches;
     CK(cudaGetLastError());
     CUtensorMap tm_q, tm_db;
     CKI(make_tmap_bf16(&tm_q, ix->g_qb, (uint64_t)((m_tiles + 1) / 2 * 2) * G3_BLOCK_M, (uint32_t)kpad, G3_BLOCK_M));
-    CKI(make_tmap_bf16(&tm_db, ix->sh_rows, n, (uint32_t)kpad, G3_BLOCK_N / cg));
+    CKI(make_tmap_bf16(&tm_db, ix->sh_rows, streamed ? (uint64_t)S : n, (uint32_t)kpad, G3_BLOCK_N / cg));
+    const size_t C2 = S / 2;  // streamed: rows per chunk buffer
+    CUtensorMap tm_half[2];
+    if (streamed)
+        for (int b = 0; b < 2; ++b)
+            CKI(make_tmap_bf16(&tm_half[b], ix->sh_rows + (size_t)b * C2 * kpad, (uint64_t)C2, (uint32_t)kpad, G3_BLOCK_N / cg));
     const bool masked = ix->cur_mask != nullptr;
     typedef void (*GemmFn)(const CUtensorMap, const CUtensorMap, const GemmParams);
     // [mode]: the tile-maxima pass and the emit pass are separate instantiations (no mode branches in the epilogue)
@@ -1656,10 +1722,10 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
                 : (masked ? gemm_topk_kernel<2, true, G3_MODE_EMIT> : gemm_topk_kernel<2, false, G3_MODE_EMIT>)};
     const size_t gsmem = cg == 1 ? G3Cfg<1>::kSmemBytes : G3Cfg<2>::kSmemBytes;
     for (GemmFn f : gfns) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-    auto launch_gemm = [&](const GemmParams& g) -> int {
+    auto launch_gemm = [&](const GemmParams& g, const CUtensorMap& tm_rows) -> int {
         GemmFn gfn = gfns[g.mode == G3_MODE_EMIT ? 1 : 0];
         if (cg == 1) {
-            gfn<<<ix->num_sms, G3_THREADS, gsmem, st>>>(tm_q, tm_db, g);
+            gfn<<<ix->num_sms, G3_THREADS, gsmem, st>>>(tm_q, tm_rows, g);
         } else {
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof cfg);
@@ -1674,7 +1740,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            CK(cudaLaunchKernelEx(&cfg, gfn, tm_q, tm_db, g));
+            CK(cudaLaunchKernelEx(&cfg, gfn, tm_q, tm_rows, g));
         }
         ++ix->launches;
         CK(cudaGetLastError());
@@ -1708,8 +1774,21 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     gp.tile_first = 0;
     gp.tile_stride = stride;
     gp.tile_count = T;
+    gp.src_tile_first = 0;
+    gp.src_tile_stride = stride;
+    const int aug_rows = ix->metric == B200_METRIC_L2 ? 1 : 0;
     CK(cudaEventRecord(ev[0], st));
-    CKI(launch_gemm(gp));
+    if (streamed) {
+        // the sampled tiles, packed back to back into the scratch; the maximum row norm is re-collected by the
+        // chunks of pass 2, which convert every row
+        CK(cudaMemsetAsync(ix->sh_maxnorm, 0, sizeof(unsigned int), st));
+        shadow_rows_kernel<<<ix->num_sms * 4, 256, 0, st>>>(ix->rows, ix->pitch, ix->store, (uint64_t)T * G3_BLOCK_N, n, stride, ix->d, kpad,
+                                                            aug_rows, ix->sh_rows, nullptr, ix->sh_maxnorm);
+        ++ix->launches;
+        CK(cudaGetLastError());
+        gp.src_tile_stride = 1;
+    }
+    CKI(launch_gemm(gp, tm_db));
     {
         // expected emissions per query = emit_factor * k.  The rank-th largest of the sampled
         // 32-row group maxima estimates the score quantile (sample rows / n) * that count; the rank
@@ -1726,9 +1805,42 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     CK(cudaMemsetAsync(ix->g_count, 0, (size_t)nq * 4, st));
     gp.mode = G3_MODE_EMIT;
     gp.tile_stride = 1;
-    gp.tile_count = NT;
+    gp.src_tile_stride = 1;
     CK(cudaEventRecord(ev[1], st));
-    CKI(launch_gemm(gp));
+    if (!streamed) {
+        gp.tile_first = gp.src_tile_first = 0;
+        gp.tile_count = NT;
+        CKI(launch_gemm(gp, tm_db));
+    } else {
+        // streamed shadow: the fp32 rows are rounded chunk by chunk into the two halves of the scratch; the converter
+        // runs on a second stream, so chunk c+1 is converted (HBM-bound) while the GEMM sweeps chunk c
+        if (!ix->sh_stream2) CK(cudaStreamCreateWithFlags(&ix->sh_stream2, cudaStreamNonBlocking));
+        for (int i = 0; i < 5; ++i)
+            if (!ix->sh_ev[i]) CK(cudaEventCreateWithFlags(&ix->sh_ev[i], cudaEventDisableTiming));
+        cudaStream_t s2 = ix->sh_stream2;
+        CK(cudaEventRecord(ix->sh_ev[4], st));  // fork: the threshold pass (which used the whole scratch) is enqueued
+        CK(cudaStreamWaitEvent(s2, ix->sh_ev[4], 0));
+        uint64_t c = 0;
+        for (uint64_t r0 = 0; r0 < n; r0 += C2, ++c) {
+            const int b = (int)(c & 1);
+            const uint64_t rows_c = std::min<uint64_t>(C2, n - r0);
+            if (c >= 2) CK(cudaStreamWaitEvent(s2, ix->sh_ev[2 + b], 0));  // the sweep that last read this half is done
+            // 2 CTAs of 256 threads x 64 registers per SM (16 warps with 4 KB in flight each): the GEMM's CTA (192 threads
+            // x 120 registers, one per SM) must find thread slots and registers beside them
+            shadow_rows_kernel<<<ix->num_sms * 2, 256, 0, s2>>>(ix->rows + r0 * ix->pitch, ix->pitch, ix->store, rows_c, rows_c, 1, ix->d,
+                                                                kpad, aug_rows, ix->sh_rows + (size_t)b * C2 * kpad, nullptr, ix->sh_maxnorm);
+            ++ix->launches;
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ix->sh_ev[b], s2));
+            CK(cudaStreamWaitEvent(st, ix->sh_ev[b], 0));
+            gp.tile_first = (uint32_t)(r0 / G3_BLOCK_N);
+            gp.src_tile_first = 0;
+            gp.tile_count = (uint32_t)((rows_c + G3_BLOCK_N - 1) / G3_BLOCK_N);
+            CKI(launch_gemm(gp, tm_half[b]));
+            CK(cudaEventRecord(ix->sh_ev[2 + b], st));
+        }
+    }
+    ix->stat_gemm_streamed = streamed ? 1 : 0;
     CK(cudaEventRecord(ev[2], st));
     // ---- exact re-rank + certificate ----
     RerankParams rp;
@@ -1896,10 +2008,11 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
     ix->stat_gemm_used = 0;
     if (!fullrank) {
         if (use_gemm) {
-            // K3 in blocks of at most 16384 queries (bounds the candidate scratch)
+            // K3 in blocks of at most 16384 queries (bounds the candidate and sample scratch)
             int rc = 0;
-            for (int64_t q0 = 0; q0 < nq && rc == 0; q0 += 16384) {
-                int64_t nb = std::min<int64_t>(16384, nq - q0);
+            const int64_t qblock = gemm_query_block(ix);
+            for (int64_t q0 = 0; q0 < nq && rc == 0; q0 += qblock) {
+                int64_t nb = std::min<int64_t>(qblock, nq - q0);
                 rc = search_gemm(ix, q_dev + (size_t)q0 * ix->d, nb, k, D_dev + (size_t)q0 * k, I_dev + (size_t)q0 * k, st);
             }
             if (rc != 2) return rc;
@@ -2337,8 +2450,9 @@ extern "C" int b200_index_search_shard_dev(b200_index* ix, const float* q_dev, i
             q_dev = ix->qn_dev;
         }
         int rc = 0;
-        for (int64_t q0 = 0; q0 < nq && rc == 0; q0 += 16384) {
-            const int64_t nb = std::min<int64_t>(16384, nq - q0);
+        const int64_t qblock = gemm_query_block(ix);
+        for (int64_t q0 = 0; q0 < nq && rc == 0; q0 += qblock) {
+            const int64_t nb = std::min<int64_t>(qblock, nq - q0);
             rc = search_gemm(ix, q_dev + (size_t)q0 * ix->d, nb, k, D_dev + (size_t)q0 * k, I_dev + (size_t)q0 * k, st,
                              widen ? 1 : 0, bound_dev + q0, world);
             if (rc == 2 && q0 != 0) return fail("the bf16 shadow disappeared between two blocks of one batch");

@@ -41,9 +41,11 @@ struct GemmParams {
     uint32_t m_tiles;       // ceil(nq / 128)
     uint64_t n;             // database rows
     uint32_t k_blocks;      // d_pad64 / 64
-    uint32_t tile_first;    // first 256-row tile of this pass
+    uint32_t tile_first;    // first 256-row tile of this pass (database row = tile * 256)
     uint32_t tile_stride;   // tile step (sampling)
     uint32_t tile_count;    // tiles in this pass
+    uint32_t src_tile_first;   // where pass tile t sits in the bf16 matrix behind tm_db: src_tile_first + t * src_tile_stride
+    uint32_t src_tile_stride;  // (the resident shadow: same as tile_first / tile_stride; a streamed chunk: 0 / 1)
     uint32_t chunk_tiles;   // tiles per work unit (L2 reuse window)
     int mode;
     const float* theta;     // [nq] emission thresholds (EMIT)
@@ -279,7 +281,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 const uint32_t t0 = chunk * p.chunk_tiles;
                 const uint32_t t1 = min(t0 + p.chunk_tiles, p.tile_count);
                 for (uint32_t t = t0; t < t1; ++t) {
-                    const uint32_t ntile = p.tile_first + t * p.tile_stride;
+                    const uint32_t ntile = p.src_tile_first + t * p.src_tile_stride;
                     for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
@@ -442,22 +444,65 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 // aug: 0 = none; 1 = database row for L2: columns d, d+1 hold h = |y|^2 / 2 split into two bf16
 // (hi + lo, residual <= 2^-16 h); 2 = query for L2: columns d, d+1 hold -1.  With these the same
 // GEMM yields q.y - |y|^2/2 = (|q|^2 - L2) / 2: larger is better, exactly like IP.
+// gather_stride > 1: output row r is database row ((r >> 8) * gather_stride << 8) + (r & 255) — the sampled 256-row
+// tiles of the threshold pass packed back to back (streamed shadow).  fp32 rows with d % 4 == 0 take the vector
+// path: 128-bit loads marked evict-first in L2 (the rows are read once; the bf16 chunk written here is what the
+// GEMM re-reads), 64-bit bf16x4 stores.
 __global__ void __launch_bounds__(256)
-shadow_rows_kernel(const uint8_t* __restrict__ rows, uint64_t pitch, int store, uint64_t n, int d, int kpad, int aug,
-                   __nv_bfloat16* __restrict__ out, float* __restrict__ norm2, unsigned int* __restrict__ max_norm2_bits) {
+shadow_rows_kernel(const uint8_t* __restrict__ rows, uint64_t pitch, int store, uint64_t n_out, uint64_t n_src, uint32_t gather_stride,
+                   int d, int kpad, int aug, __nv_bfloat16* __restrict__ out, float* __restrict__ norm2,
+                   unsigned int* __restrict__ max_norm2_bits) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t warps_total = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const bool vec = store == 0 && (d & 3) == 0 && (pitch & 15) == 0;
+    const uint64_t pol = l2_policy_evict_first();
     float wmax = 0.0f;
-    for (uint64_t r = warp_global; r < n; r += warps_total) {
-        const uint8_t* src = rows + r * pitch;
+    for (uint64_t r = warp_global; r < n_out; r += warps_total) {
+        const uint64_t sr = gather_stride > 1 ? ((((r >> 8) * gather_stride) << 8) + (r & 255)) : r;
         __nv_bfloat16* dst = out + r * (uint64_t)kpad;
         float acc = 0.0f;
-        for (int c = lane; c < kpad; c += 32) {
-            float v = 0.0f;
-            if (c < d) v = store == 0 ? reinterpret_cast<const float*>(src)[c] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[c]);
-            acc = fmaf(v, v, acc);
-            dst[c] = __float2bfloat16_rn(v);
+        if (sr >= n_src) {  // past the end of the database: a zero row (never a candidate: the epilogue masks it)
+            for (int c = lane; c < kpad; c += 32) dst[c] = __float2bfloat16_rn(0.0f);
+            continue;
+        }
+        const uint8_t* src = rows + sr * pitch;
+        if (vec) {
+            // all of this lane's 128-bit loads of the row are issued before the first is used (8 per pass: rows of up
+            // to 1024 columns in one pass), so a warp keeps up to 4 KB in flight
+            for (int base4 = 0; base4 < (kpad >> 2); base4 += 256) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c4 = base4 + lane + 32 * u;
+                    v[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (c4 < (kpad >> 2) && 4 * c4 < d)
+                        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                                     : "l"(src + 16 * (size_t)c4), "l"(pol));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c4 = base4 + lane + 32 * u;
+                    if (c4 >= (kpad >> 2)) break;
+                    acc = fmaf(v[u].x, v[u].x, acc);
+                    acc = fmaf(v[u].y, v[u].y, acc);
+                    acc = fmaf(v[u].z, v[u].z, acc);
+                    acc = fmaf(v[u].w, v[u].w, acc);
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y), hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(dst + 4 * c4) = pk;
+                }
+            }
+        } else {
+            for (int c = lane; c < kpad; c += 32) {
+                float v = 0.0f;
+                if (c < d) v = store == 0 ? reinterpret_cast<const float*>(src)[c] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[c]);
+                acc = fmaf(v, v, acc);
+                dst[c] = __float2bfloat16_rn(v);
+            }
         }
         acc = warp_sum_xor(acc);
         __syncwarp();

@@ -183,3 +183,40 @@ def test_batched_masked_search(b200, metric):
     mask[[5, 77, 4000]] = True
     D, I = idx.search(q, k, row_mask=mask)
     assert (I[:, 3:] == -1).all() and set(I[0, :3].tolist()) == {12, 84, 4007}
+
+
+@pytest.mark.parametrize("n,d,nq,k,metric,store,cap", [
+    (200_000, 384, 100, 10, 1, "f32", 65_536),   # 4 chunks, the last one ragged (3392 rows = 13.25 tiles)
+    (150_001, 768, 64, 100, 0, "f32", 32_768),   # odd row count: a ragged tile inside the last chunk
+    (120_000, 100, 70, 10, 0, "f32", 20_000),    # cap rounds down to whole 256-row tiles; vector path with zero padded K
+    (90_000, 50, 40, 5, 1, "f32", 30_000),       # d % 4 != 0: the scalar conversion path
+    (100_000, 512, 48, 10, 0, "bf16", 25_600),   # bf16 rows
+])
+def test_streamed_shadow_when_it_does_not_fit(b200, n, d, nq, k, metric, store, cap):
+    """When the bf16 shadow cannot stay resident (100M x 384 fp32 fills the GPU; here: option gemm_shadow_max_rows) the
+    rows are rounded chunk by chunk into an L2-sized scratch and swept while hot — same candidates, same exact re-rank,
+    same certificate, so ids and distances stay bit-identical to the scan path."""
+    st = run_case(b200, n, d, nq, k, metric=metric, store=store, dup=True, ids=True, gemm_shadow_max_rows=cap)
+    assert st["stat_gemm_used"] == 1
+    assert st["stat_gemm_fallbacks"] <= nq // 4, st
+
+
+def test_streamed_shadow_masked_and_toggled(b200):
+    n, d, nq, k = 130_000, 128, 33, 10
+    db, q = oracle.synth_rows(n, d, 15), oracle.synth_rows(nq, d, 16)
+    idx = b200.IndexFlat(d, 0)
+    idx.add(db)
+    Dw, Iw = oracle.search(0, db, q, k, order=oracle.ORDER_DEVICE)
+    for cap in (0, 40_000, 0, 16_384):  # resident -> streamed -> resident -> streamed with another chunk size
+        idx.set_option("gemm_shadow_max_rows", cap)
+        D, I = idx.search(q, k)
+        assert idx.get_option("stat_gemm_used") == 1 and idx.get_option("stat_gemm_streamed") == (1 if cap else 0)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)
+    mask = np.random.default_rng(3).random(n) < 0.3
+    rows = np.nonzero(mask)[0]
+    D, I = idx.search(q, k, row_mask=mask)
+    assert idx.get_option("stat_gemm_streamed") == 1
+    Dm, Im = oracle.search(0, db[rows], q, k, ids=rows.astype(np.int64), order=oracle.ORDER_DEVICE)
+    np.testing.assert_array_equal(I, Im)
+    np.testing.assert_array_equal(D, Dm)
