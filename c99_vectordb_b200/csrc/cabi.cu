@@ -111,11 +111,12 @@ struct b200_index {
             opt_claim_min = 0, opt_claim_first = 0, opt_pdl = 1, opt_queries_stable = 0, opt_phase_stamps = 0, opt_fuse_query_norm = 1;
     bool cur_norm_q = false;  // the scan launches of the search in flight normalise their queries themselves
     int64_t opt_gemm_min_rows = 4096, opt_gemm_min_nq = 2, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2,
-            opt_gemm_shadow_max_rows = 0;  // > 0: keep at most this many rows of the bf16 shadow resident (streamed beyond; tests)
+            opt_gemm_shadow_max_rows = 0,  // > 0: keep at most this many rows of the bf16 shadow resident (streamed beyond; tests)
+            opt_prefilter = 0;             // 1: single queries rank the bf16 shadow first (half the bytes), then re-rank exactly
     // read-only statistics of the last batched (K3) search
     int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
             stat_gemm_pass2_us = 0, stat_gemm_rerank_us = 0, stat_gemm_scan_fallbacks = 0, stat_gemm_pre_us = 0,
-            stat_gemm_host_us = 0, stat_gemm_streamed = 0;
+            stat_gemm_host_us = 0, stat_gemm_streamed = 0, stat_prefilter_used = 0, stat_prefilter_fallbacks = 0;
     // K3 state
     __nv_bfloat16* sh_rows = nullptr;  // bf16 shadow of the rows [ntotal, kpad]
     float* sh_norm2 = nullptr;
@@ -123,6 +124,9 @@ struct b200_index {
     int64_t sh_valid_rows = -1;        // rows covered by the shadow (-1 = none)
     int64_t sh_failed_rows = -1;       // ntotal at which the shadow allocation last failed (no retry until it changes)
     size_t sh_cap_rows = 0;
+    uint8_t* pf_buf = nullptr;         // scratch of the single-query pre-filter (lists, thresholds, extended query)
+    size_t pf_cap = 0;
+    int* pf_cert_host = nullptr;       // pinned: the certificate of the last pre-filtered search
     bool sh_streamed = false;          // the shadow does not fit: sh_rows is a scratch of sh_cap_rows rows, refilled chunk by chunk per search
     cudaStream_t sh_stream2 = nullptr; // streamed shadow: the converter of chunk c+1 runs here while the GEMM sweeps chunk c
     cudaEvent_t sh_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0,1] chunk converted, [2,3] chunk swept, [4] fork
@@ -296,6 +300,8 @@ extern "C" int b200_index_destroy(b200_index* ix) {
     cudaFree(ix->idbits_dev);
     cudaFree(ix->ids_minmax_dev);
     cudaFree(ix->sh_rows);
+    cudaFree(ix->pf_buf);
+    if (ix->pf_cert_host) cudaFreeHost(ix->pf_cert_host);
     if (ix->sh_stream2) cudaStreamDestroy(ix->sh_stream2);
     for (int i = 0; i < 5; ++i)
         if (ix->sh_ev[i]) cudaEventDestroy(ix->sh_ev[i]);
@@ -398,6 +404,9 @@ static const OptName kOpts[] = {
     {"gemm_sample_tiles", &b200_index::opt_gemm_sample_tiles},
     {"gemm_cta_group", &b200_index::opt_gemm_cta_group},
     {"gemm_shadow_max_rows", &b200_index::opt_gemm_shadow_max_rows},
+    {"prefilter", &b200_index::opt_prefilter},
+    {"stat_prefilter_used", &b200_index::stat_prefilter_used},
+    {"stat_prefilter_fallbacks", &b200_index::stat_prefilter_fallbacks},
     {"stat_gemm_streamed", &b200_index::stat_gemm_streamed},
     {"stat_gemm_used", &b200_index::stat_gemm_used},
     {"stat_gemm_fallbacks", &b200_index::stat_gemm_fallbacks},
@@ -1949,6 +1958,119 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
 }
 
 
+// Single-query pre-filter (option `prefilter`, off by default — the fp32 scan is the path north_star names and the
+// one the headline measures).  The SAME scan kernel ranks the resident bf16 shadow (half the bytes of the fp32 rows;
+// inner product, for L2 through the two augmented columns carrying |y|^2/2 against -1 in the query) and returns its best
+// kp = max(32, 4k) rows; those are re-scored from the fp32 rows with the scan's exact arithmetic (rerank_kernel) and the
+// answer is accepted only under the same certificate as the batched path: every row outside the list has approximate
+// score <= theta = the kp-th approximate score, hence exact score <= theta + eps with eps = 2^-9 |q||y| (one bf16
+// rounding per row element, queries stay fp32) + accumulation slack, so nothing outside can reach the top k when the
+// k-th exact score beats that.  Returns 0 = D/I hold the proven exact answer, 2 = not applicable or not certified
+// (the caller runs the fp32 scan).  One host read of the 4-byte certificate per search.
+static int search_prefilter(b200_index* ix, const float* q_dev, int64_t k, float* D_dev, int64_t* I_dev, cudaStream_t st) {
+    const int kp = (int)std::min<int64_t>(B200_FUSED_K_MAX, std::max<int64_t>(32, 4 * k));
+    if (4 * k > B200_FUSED_K_MAX || ix->ntotal < 16 * kp || ix->cur_mask || ix->xchg_active || ix->d < 32) return 2;
+    if (ensure_shadow(ix, st) != 0) return 2;  // resident shadows only
+    const int kpad = gemm_kpad(ix);
+    const bool l2 = ix->metric == B200_METRIC_L2;
+    const int dv = ix->d + (l2 ? 2 : 0);
+    // scratch: Dp[kp] f32 | Ip[kp] i64 | cand[kp] u32 | count, theta, qn2, cert | q'[dv]
+    const size_t off_I = 256 * 4, off_c = off_I + 256 * 8, off_s = off_c + 256 * 4, off_q = off_s + 64;
+    const size_t qx_floats = (size_t)((ix->d + 3) & ~3);
+    const size_t need = off_q + (qx_floats + (size_t)dv + 8) * 4;
+    if (ix->pf_cap < need) {
+        CK(cudaStreamSynchronize(st));
+        CKI(grow(&ix->pf_buf, &ix->pf_cap, need));
+    }
+    if (!ix->pf_cert_host) CK(cudaHostAlloc((void**)&ix->pf_cert_host, 64, cudaHostAllocDefault));
+    float* Dp = (float*)ix->pf_buf;
+    int64_t* Ip = (int64_t*)(ix->pf_buf + off_I);
+    uint32_t* cand = (uint32_t*)(ix->pf_buf + off_c);
+    unsigned int* count = (unsigned int*)(ix->pf_buf + off_s);
+    float* theta = (float*)(ix->pf_buf + off_s + 16);
+    float* qn2 = (float*)(ix->pf_buf + off_s + 32);
+    int* cert = (int*)(ix->pf_buf + off_s + 48);
+    float* qx = (float*)(ix->pf_buf + off_q);
+    const float* q_scan = q_dev;
+    if (ix->cur_norm_q) {  // cosine, normalisation deferred to the scan's prologue by the caller: K1 on the query here
+                           // (the view below scans with another logical dimension)
+        CKI(ingest_dev(ix->d, ix->d, B200_STORE_F32, q_dev, (uint8_t*)qx, (size_t)ix->d * 4, 1, 1, ix->num_sms, st, &ix->launches));
+        q_scan = qx;
+    }
+    const float* q_exact = q_scan;  // what the re-rank scores against (the normalised fp32 query)
+    if (l2) {
+        float* qe = qx + qx_floats;
+        extend_query_kernel<<<(unsigned)((dv + 255) / 256), 256, 0, st>>>(q_scan, 1, ix->d, qe);
+        ++ix->launches;
+        q_scan = qe;
+    }
+    {
+        // the scan kernel over the shadow: a view of the index with bf16 rows of kpad columns, inner product, no id map
+        struct View {
+            b200_index* ix;
+            uint8_t* rows; size_t pitch; int store, metric, d, d_pad, lpr, ids_state; bool norm_q;
+            ~View() {
+                ix->rows = rows; ix->pitch = pitch; ix->store = store; ix->metric = metric; ix->d = d; ix->d_pad = d_pad;
+                ix->lpr = lpr; ix->ids_state = ids_state; ix->cur_norm_q = norm_q;
+            }
+        } view{ix, ix->rows, ix->pitch, ix->store, ix->metric, ix->d, ix->d_pad, ix->lpr, ix->ids_state, ix->cur_norm_q};
+        ix->rows = (uint8_t*)ix->sh_rows;
+        ix->pitch = (size_t)kpad * 2;
+        ix->store = B200_STORE_BF16;
+        ix->metric = B200_METRIC_IP;
+        ix->d = dv;
+        ix->d_pad = kpad;
+        ix->lpr = pick_lpr((size_t)kpad * 2 / 16);
+        ix->ids_state = 0;
+        ix->cur_norm_q = false;
+        ScanPlan pl;
+        CKI(plan_scan(ix, 1, kp, false, &pl));
+        CKI(launch_scan(ix, pl, q_scan, 1, kp, Dp, Ip, nullptr, st));
+    }
+    prefilter_lists_kernel<<<1, 256, 0, st>>>(Dp, Ip, kp, q_exact, ix->d, ix->d, cand, count, theta, qn2);
+    ++ix->launches;
+    RerankParams rp;
+    memset(&rp, 0, sizeof rp);
+    rp.rows = ix->rows;
+    rp.pitch_bytes = ix->pitch;
+    rp.nvec = (uint32_t)(ix->pitch / 16);
+    rp.store = ix->store;
+    rp.d = ix->d;
+    rp.qstride = (ix->d_pad + 7) / 8 * 8;
+    rp.lpr = ix->lpr;
+    rp.q = q_exact;
+    rp.cand_rows = cand;
+    rp.cand_count = count;
+    rp.cand_cap = (uint32_t)kp;
+    rp.theta = theta;
+    rp.qnorm2 = qn2;
+    rp.max_norm2_bits = ix->sh_maxnorm;
+    // one bf16 rounding per row element (u = 2^-9 relative, the query stays fp32) + fp32 accumulation slack of both sums
+    rp.eps_rel = 0.001953125f * 1.001f + 2.0f * (float)ix->d * 1.2e-7f + 1e-5f;
+    rp.n = (uint64_t)ix->ntotal;
+    rp.k = (int)k;
+    rp.id_map = ix->ids_state == 1 ? ix->ids : nullptr;
+    rp.D = D_dev;
+    rp.I = I_dev;
+    rp.certified = cert;
+    const size_t rsmem = (size_t)rp.qstride * 4 + (size_t)next_pow2((uint32_t)std::max(kp, 2)) * 8 + 64;
+    if (l2) {
+        CK(cudaFuncSetAttribute(rerank_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        rerank_kernel<1><<<1, 256, rsmem, st>>>(rp);
+    } else {
+        CK(cudaFuncSetAttribute(rerank_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        rerank_kernel<0><<<1, 256, rsmem, st>>>(rp);
+    }
+    ++ix->launches;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ix->pf_cert_host, cert, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ix->stat_prefilter_used = 1;
+    if (*ix->pf_cert_host == 1) return 0;
+    ++ix->stat_prefilter_fallbacks;
+    return 2;
+}
+
 static int search_scan_block(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev, int64_t* I_dev,
                              cudaStream_t st) {
     int64_t q0 = 0;
@@ -2006,6 +2128,11 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
         }
     }
     ix->stat_gemm_used = 0;
+    ix->stat_prefilter_used = 0;
+    if (!fullrank && !use_gemm && nq == 1 && ix->opt_prefilter) {
+        const int rc = search_prefilter(ix, q_dev, k, D_dev, I_dev, st);
+        if (rc != 2) return rc;
+    }
     if (!fullrank) {
         if (use_gemm) {
             // K3 in blocks of at most 16384 queries (bounds the candidate and sample scratch)

@@ -713,3 +713,53 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
         }
     }
 }
+
+// ---- single-query pre-filter (option `prefilter`): lists of the approximate scan -> re-rank inputs -------------
+// The scan kernel has just ranked the bf16 shadow for query q: Dp/Ip[q, 0..kp) = its best kp rows by approximate
+// score (row positions, best-first, padded with -1).  This turns them into the candidate list, the threshold
+// theta[q] = the kp-th approximate score (every row outside the list scores no better; -inf when the list holds every
+// valid row) and |q|^2 for the re-rank kernel's certificate.  aug != 0: the query was extended by two -1 columns (L2
+// through q.y - |y|^2/2); they do not count towards |q|^2.  One CTA per query.
+__global__ void __launch_bounds__(256)
+prefilter_lists_kernel(const float* __restrict__ Dp, const int64_t* __restrict__ Ip, int kp, const float* __restrict__ q, int d, int qld,
+                       uint32_t* __restrict__ cand_rows, unsigned int* __restrict__ cand_count, float* __restrict__ theta,
+                       float* __restrict__ qnorm2) {
+    __shared__ float red[8];
+    __shared__ unsigned int cnt;
+    const int qi = blockIdx.x;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    unsigned int mine = 0;
+    for (int j = threadIdx.x; j < kp; j += blockDim.x) {
+        const int64_t r = Ip[(size_t)qi * kp + j];
+        if (r >= 0) {
+            cand_rows[(size_t)qi * kp + j] = (uint32_t)r;  // valid entries are a prefix of the list
+            ++mine;
+        }
+    }
+    if (mine) atomicAdd(&cnt, mine);
+    float acc = 0.0f;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        const float v = q[(size_t)qi * qld + i];
+        acc = fmaf(v, v, acc);
+    }
+    acc = warp_sum_xor(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        qnorm2[qi] = t;
+        cand_count[qi] = cnt;
+        theta[qi] = cnt == (unsigned)kp ? Dp[(size_t)qi * kp + kp - 1] : -INFINITY;
+    }
+}
+
+// q'[nq, d + 2] = [q, -1, -1]: the extended query of the L2 pre-filter
+__global__ void extend_query_kernel(const float* __restrict__ q, int64_t nq, int d, float* __restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq * (d + 2)) return;
+    const int64_t qi = t / (d + 2);
+    const int c = (int)(t - qi * (d + 2));
+    out[t] = c < d ? q[qi * d + c] : -1.0f;
+}

@@ -74,9 +74,18 @@ int b200_index_reserve(b200_index* ix, int64_t n_total);
  *                         cross PCIe through the pinned ring with threaded host copies; 0: plain copies
  *   gemm_min_nq           batched tensor-core path (K3) for nq >= this (default 2; 0 disables)
  *   gemm_min_rows, gemm_emit_factor, gemm_sample_tiles, gemm_chunk_tiles, gemm_cta_group (1|2)
- * Read-only statistics of the last search (b200_index_get_option): stat_gemm_used,
+ *   gemm_shadow_max_rows  > 0: keep at most this many rows of K3's bf16 shadow resident and stream the rest through it
+ *                         chunk by chunk (what happens by itself when the shadow does not fit next to the rows)
+ *   prefilter             1: single queries (k <= 64, unfiltered) rank the resident bf16 shadow with the scan kernel
+ *                         first — half the bytes of the fp32 rows — re-score the best max(32, 4k) rows from the fp32
+ *                         rows and accept the answer only when a certificate proves it exact; otherwise the fp32 scan
+ *                         runs.  Same ids and distances as the default (0) either way; costs the shadow (+50 % memory)
+ *                         and one 4-byte host read per search
+ *   scan_pdl, queries_stable   programmatic dependent launch of back-to-back searches (see b200_index_search_dev)
+ * Read-only statistics of the last search (b200_index_get_option): stat_gemm_used, stat_gemm_streamed,
  *   stat_gemm_fallbacks (queries retried), stat_gemm_scan_fallbacks (queries recomputed by the scan),
- *   stat_gemm_cand_total, stat_gemm_pass1_us, stat_gemm_pass2_us, stat_gemm_rerank_us. */
+ *   stat_gemm_cand_total, stat_gemm_pass1_us, stat_gemm_pass2_us, stat_gemm_rerank_us, stat_prefilter_used,
+ *   stat_prefilter_fallbacks (searches the certificate sent to the fp32 scan, cumulative). */
 int b200_index_set_option(b200_index* ix, const char* name, int64_t value);
 int b200_index_get_option(b200_index* ix, const char* name, int64_t* out_value);
 
