@@ -112,11 +112,13 @@ struct b200_index {
     bool cur_norm_q = false;  // the scan launches of the search in flight normalise their queries themselves
     int64_t opt_gemm_min_rows = 4096, opt_gemm_min_nq = 2, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2,
             opt_gemm_shadow_max_rows = 0,  // > 0: keep at most this many rows of the bf16 shadow resident (streamed beyond; tests)
-            opt_prefilter = 0;             // 1: single queries rank the bf16 shadow first (half the bytes), then re-rank exactly
+            opt_prefilter = 0,             // 1: single queries rank the bf16 shadow first (half the bytes), then re-rank exactly
+            opt_gemm_rows_form = 1;        // small batches: rows as the M operand, queries resident in shared memory (0: always the 256 x 256 form)
     // read-only statistics of the last batched (K3) search
     int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
             stat_gemm_pass2_us = 0, stat_gemm_rerank_us = 0, stat_gemm_scan_fallbacks = 0, stat_gemm_pre_us = 0,
-            stat_gemm_host_us = 0, stat_gemm_streamed = 0, stat_prefilter_used = 0, stat_prefilter_fallbacks = 0;
+            stat_gemm_host_us = 0, stat_gemm_streamed = 0, stat_prefilter_used = 0, stat_prefilter_fallbacks = 0,
+            stat_gemm_rows_form = 0;
     // K3 state
     __nv_bfloat16* sh_rows = nullptr;  // bf16 shadow of the rows [ntotal, kpad]
     float* sh_norm2 = nullptr;
@@ -405,6 +407,8 @@ static const OptName kOpts[] = {
     {"gemm_cta_group", &b200_index::opt_gemm_cta_group},
     {"gemm_shadow_max_rows", &b200_index::opt_gemm_shadow_max_rows},
     {"prefilter", &b200_index::opt_prefilter},
+    {"gemm_rows_form", &b200_index::opt_gemm_rows_form},
+    {"stat_gemm_rows_form", &b200_index::stat_gemm_rows_form},
     {"stat_prefilter_used", &b200_index::stat_prefilter_used},
     {"stat_prefilter_fallbacks", &b200_index::stat_prefilter_fallbacks},
     {"stat_gemm_streamed", &b200_index::stat_gemm_streamed},
@@ -1181,6 +1185,20 @@ extern "C" int b200_index_add_synthetic(b200_index* ix, int64_t n, uint64_t seed
 // ---------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------
+// What a scan launch reads: the index's own rows by default; the single-query pre-filter scans the bf16 shadow
+// through another view (search_prefilter).
+struct ScanView {
+    const uint8_t* rows;
+    size_t pitch;
+    int store, metric, d, d_pad, lpr;
+    const int64_t* id_map;  // row -> record id, or null (row positions)
+    bool normalize_q;       // L2-normalise the queries while staging them
+};
+static ScanView index_view(const b200_index* ix) {
+    return ScanView{ix->rows, ix->pitch, ix->store, ix->metric, ix->d, ix->d_pad, ix->lpr,
+                    ix->ids_state == 1 ? ix->ids : nullptr, ix->cur_norm_q};
+}
+
 struct ScanPlan {
     int variant = 0, nw = 0, qb = 0;
     uint32_t tile_rows = 0, stages = 0, tile_bytes = 0, scratch_keys = 0;
@@ -1233,13 +1251,14 @@ static uint32_t next_pow2(uint32_t v) {
     return m;
 }
 
-static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out) {
+static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out, const ScanView* view = nullptr) {
+    const ScanView v = view ? *view : index_view(ix);
     ScanPlan pl;
     pl.qb = qb;
-    const int qstride = (ix->d_pad + 7) / 8 * 8;
+    const int qstride = (v.d_pad + 7) / 8 * 8;
     const int kk = fullrank ? 1 : k;
     size_t budget = ix->smem_optin - 1024;
-    const uint32_t step_rows = SCAN_RB * (32u / (uint32_t)ix->lpr);  // rows one warp step covers
+    const uint32_t step_rows = SCAN_RB * (32u / (uint32_t)v.lpr);  // rows one warp step covers
     int variant = (int)ix->opt_variant;
     // AUTO (measured over d = 64..2048, fp32 and bf16: profiles/README.md, r1_sweep11_*, r1_sweep13_*):
     // the TMA-staged ring with dynamic tiles and as many warps as fit (<= 16) x 2 stages.  Short rows
@@ -1249,7 +1268,7 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
     // d=32 fp32 1.09, bf16 d=64 1.07, bf16 d=128 0.99-1.05 vs 0.82-1.00 for direct loads); other rows under 512
     // bytes go to the direct-load variant with its 32 resident warps/SM.
     const bool auto_variant = variant == B200_SCAN_AUTO;
-    if (auto_variant) variant = (ix->pitch >= 512 || ix->lpr == 8) ? B200_VARIANT_BULK : B200_VARIANT_LDG;
+    if (auto_variant) variant = (v.pitch >= 512 || v.lpr == 8) ? B200_VARIANT_BULK : B200_VARIANT_LDG;
     if (variant == B200_VARIANT_BULK) {
         // CTAs per SM (option scan_ctas_per_sm, default 1): c co-resident CTAs share the SM's shared memory and warp
         // slots, so that at a launch boundary (programmatic dependent launch) an SM is handed over one CTA at a time
@@ -1269,10 +1288,10 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
             if (ix->opt_tile_rows > 0)
                 m_pref = (uint32_t)((ix->opt_tile_rows + step_rows - 1) / step_rows);
             else
-                m_pref = (uint32_t)std::max(1.0, 12288.0 / ((double)step_rows * ix->pitch) + 0.5);
+                m_pref = (uint32_t)std::max(1.0, 12288.0 / ((double)step_rows * v.pitch) + 0.5);
             for (uint32_t m = m_pref; m >= 1 && !ok; --m) {
                 uint32_t tr = m * step_rows;
-                uint64_t tile_bytes = (uint64_t)tr * ix->pitch;
+                uint64_t tile_bytes = (uint64_t)tr * v.pitch;
                 if (tile_bytes > (1u << 19)) continue;  // mbarrier tx-count headroom
                 const uint32_t scratch = std::max<uint32_t>(B200_FINAL_BUF_KEYS, next_pow2((uint32_t)(nw * kk)));
                 size_t fixed = scan_smem_bytes(B200_VARIANT_BULK, nw, qb, qstride, kk, fullrank, 0, 0, scratch);
@@ -1314,7 +1333,7 @@ static int plan_scan(b200_index* ix, int qb, int k, bool fullrank, ScanPlan* out
             pl.smem = smem;
             break;
         }
-        ScanFn fn = pick_scan(ix->metric, ix->store, qb, B200_VARIANT_LDG, ix->lpr);
+        ScanFn fn = pick_scan(v.metric, v.store, qb, B200_VARIANT_LDG, v.lpr);
         CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pl.nw * 32, pl.smem));
@@ -1336,19 +1355,20 @@ __global__ void fill_pad_kernel(float* D, int64_t* I, int64_t count) {
 }
 
 static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, int nqb, int k, float* D,
-                       int64_t* I, uint32_t* score_keys, cudaStream_t st) {
+                       int64_t* I, uint32_t* score_keys, cudaStream_t st, const ScanView* view = nullptr) {
+    const ScanView v = view ? *view : index_view(ix);
     ScanParams p;
     memset(&p, 0, sizeof p);
-    p.rows = ix->rows;
-    p.pitch_bytes = ix->pitch;
-    p.nvec = (uint32_t)(ix->pitch / 16);
+    p.rows = v.rows;
+    p.pitch_bytes = v.pitch;
+    p.nvec = (uint32_t)(v.pitch / 16);
     p.n = (uint64_t)ix->ntotal;
     p.q = q_dev;
-    p.d = ix->d;
-    p.qstride = (ix->d_pad + 7) / 8 * 8;
+    p.d = v.d;
+    p.qstride = (v.d_pad + 7) / 8 * 8;
     p.nqb = nqb;
     p.k = score_keys ? 1 : k;
-    p.normalize_q = ix->cur_norm_q ? 1 : 0;
+    p.normalize_q = v.normalize_q ? 1 : 0;
     const int set = (int)(ix->launch_seq++ & 1);  // control words and survivor lists of this launch's parity
     p.ticket = reinterpret_cast<unsigned int*>(ix->ctl + (size_t)set * 16);
     p.dynamic = ix->opt_dynamic < 0 ? (pl.variant == B200_VARIANT_BULK ? 1 : 0) : (ix->opt_dynamic ? 1 : 0);
@@ -1372,7 +1392,7 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     if (ix->opt_fused_tail >= 0) p.fused_tail = ix->opt_fused_tail ? 1 : 0;
     p.D = D;
     p.I = I;
-    p.id_map = ix->ids_state == 1 ? ix->ids : nullptr;
+    p.id_map = v.id_map;
     p.id_base = 0;
     p.tile_rows = pl.tile_rows;
     p.stages = pl.stages;
@@ -1413,8 +1433,8 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
         p.stamps = ix->stamps;
         ix->stamps_grid = pl.grid;
     }
-    ScanFn fn = pick_scan(ix->metric, ix->store, pl.qb, pl.variant, ix->lpr);
-    if (!fn) return fail("no scan kernel for metric=%d store=%d qb=%d variant=%d", ix->metric, ix->store, pl.qb, pl.variant);
+    ScanFn fn = pick_scan(v.metric, v.store, pl.qb, pl.variant, v.lpr);
+    if (!fn) return fail("no scan kernel for metric=%d store=%d qb=%d variant=%d", v.metric, v.store, pl.qb, pl.variant);
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     // Programmatic dependent launch: a search that follows another kernel on this stream may start while that kernel
     // drains (its CTAs take SMs as they free up).  pdl = 1: the kernel waits for its predecessor before it reads the
@@ -1435,7 +1455,7 @@ static int launch_scan(b200_index* ix, const ScanPlan& pl, const float* q_dev, i
     CK(cudaLaunchKernelEx(&cfg, fn, p));
     ++ix->launches;
     if (!score_keys && !p.fused_tail) {
-        MergeFn mf = pick_merge(ix->metric, pl.qb);
+        MergeFn mf = pick_merge(v.metric, pl.qb);
         size_t msmem = (size_t)pl.scratch_keys * 8 + 16 + B200_PREF_BYTES;
         mf<<<nqb, 256, msmem, st>>>(p, (uint32_t)pl.grid);
         ++ix->launches;
@@ -1671,6 +1691,21 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     for (int i = 0; i < 5; ++i)
         if (!ev[i]) CK(cudaEventCreate(&ev[i]));
     CK(cudaEventRecord(ev[4], st));
+    // Small batches: rows as the M operand, the queries resident in shared memory (gemm_rows_topk_kernel) when
+    // N = nq rounded up to 16 fits next to a ring of >= 4 stages.
+    const uint32_t n_cols = (uint32_t)((nq + 15) / 16 * 16);
+    uint32_t rows_stages = 0;
+    size_t rows_smem = 0;
+    if (cg == 2 && ix->opt_gemm_rows_form != 0 && n_cols <= 256) {
+        const size_t qres = (size_t)(n_cols / 2) * kpad * 2;
+        const size_t budget = ix->smem_optin - 1024 - 256 - (size_t)((n_cols + 31) & ~31u) * 4;
+        if (qres + 4 * (size_t)G3T_A_BYTES <= budget) {
+            rows_stages = (uint32_t)std::min<size_t>(8, (budget - qres) / G3T_A_BYTES);
+            rows_smem = 1024 + qres + (size_t)rows_stages * G3T_A_BYTES + (2 * rows_stages + 6) * 8 + (size_t)((n_cols + 31) & ~31u) * 4;
+        }
+    }
+    const bool rows_form = rows_stages >= 4;
+    ix->stat_gemm_rows_form = rows_form ? 1 : 0;
     // ---- scratch ----
     const size_t qb_elems = (size_t)((m_tiles + 1) / 2 * 2) * G3_BLOCK_M * kpad;  // whole 256-query groups
     // sampled tiles: each contributes 8 group maxima; at most 8192 maxima per query are sorted
@@ -1722,6 +1757,13 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
         for (int b = 0; b < 2; ++b)
             CKI(make_tmap_bf16(&tm_half[b], ix->sh_rows + (size_t)b * C2 * kpad, (uint64_t)C2, (uint32_t)kpad, G3_BLOCK_N / cg));
     const bool masked = ix->cur_mask != nullptr;
+    CUtensorMap tm_q_rows;
+    if (rows_form) CKI(make_tmap_bf16(&tm_q_rows, ix->g_qb, (uint64_t)((m_tiles + 1) / 2 * 2) * G3_BLOCK_M, (uint32_t)kpad, n_cols / 2));
+    typedef void (*GemmRowsFn)(const CUtensorMap, const CUtensorMap, const GemmRowsParams);
+    GemmRowsFn rfns[2] = {masked ? gemm_rows_topk_kernel<G3_MODE_TILEMAX, true> : gemm_rows_topk_kernel<G3_MODE_TILEMAX, false>,
+                          masked ? gemm_rows_topk_kernel<G3_MODE_EMIT, true> : gemm_rows_topk_kernel<G3_MODE_EMIT, false>};
+    if (rows_form)
+        for (GemmRowsFn f : rfns) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
     typedef void (*GemmFn)(const CUtensorMap, const CUtensorMap, const GemmParams);
     // [mode]: the tile-maxima pass and the emit pass are separate instantiations (no mode branches in the epilogue)
     GemmFn gfns[2] = {
@@ -1732,6 +1774,32 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     const size_t gsmem = cg == 1 ? G3Cfg<1>::kSmemBytes : G3Cfg<2>::kSmemBytes;
     for (GemmFn f : gfns) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
     auto launch_gemm = [&](const GemmParams& g, const CUtensorMap& tm_rows) -> int {
+        if (rows_form) {
+            GemmRowsParams r;
+            memset(&r, 0, sizeof r);
+            r.nq = g.nq; r.n_cols = n_cols; r.n = g.n; r.k_blocks = g.k_blocks;
+            r.tile_first = g.tile_first; r.tile_stride = g.tile_stride; r.tile_count = g.tile_count;
+            r.src_tile_first = g.src_tile_first; r.src_tile_stride = g.src_tile_stride;
+            r.stages = rows_stages; r.mode = g.mode; r.theta = g.theta; r.cand_count = g.cand_count; r.cand_rows = g.cand_rows;
+            r.cand_cap = g.cand_cap; r.tilemax = g.tilemax; r.row_mask = g.row_mask;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3((unsigned)(ix->num_sms / 2 * 2));
+            cfg.blockDim = dim3(G3T_THREADS);
+            cfg.dynamicSmemBytes = rows_smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&cfg, rfns[g.mode == G3_MODE_EMIT ? 1 : 0], tm_q_rows, tm_rows, r));
+            ++ix->launches;
+            CK(cudaGetLastError());
+            return 0;
+        }
         GemmFn gfn = gfns[g.mode == G3_MODE_EMIT ? 1 : 0];
         if (cg == 1) {
             gfn<<<ix->num_sms, G3_THREADS, gsmem, st>>>(tm_q, tm_rows, g);
@@ -1970,6 +2038,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
 static int search_prefilter(b200_index* ix, const float* q_dev, int64_t k, float* D_dev, int64_t* I_dev, cudaStream_t st) {
     const int kp = (int)std::min<int64_t>(B200_FUSED_K_MAX, std::max<int64_t>(32, 4 * k));
     if (4 * k > B200_FUSED_K_MAX || ix->ntotal < 16 * kp || ix->cur_mask || ix->xchg_active || ix->d < 32) return 2;
+    if (ix->store != B200_STORE_F32) return 2;  // bf16 rows: the shadow would be the same bytes again
     if (ensure_shadow(ix, st) != 0) return 2;  // resident shadows only
     const int kpad = gemm_kpad(ix);
     const bool l2 = ix->metric == B200_METRIC_L2;
@@ -2005,27 +2074,12 @@ static int search_prefilter(b200_index* ix, const float* q_dev, int64_t k, float
         q_scan = qe;
     }
     {
-        // the scan kernel over the shadow: a view of the index with bf16 rows of kpad columns, inner product, no id map
-        struct View {
-            b200_index* ix;
-            uint8_t* rows; size_t pitch; int store, metric, d, d_pad, lpr, ids_state; bool norm_q;
-            ~View() {
-                ix->rows = rows; ix->pitch = pitch; ix->store = store; ix->metric = metric; ix->d = d; ix->d_pad = d_pad;
-                ix->lpr = lpr; ix->ids_state = ids_state; ix->cur_norm_q = norm_q;
-            }
-        } view{ix, ix->rows, ix->pitch, ix->store, ix->metric, ix->d, ix->d_pad, ix->lpr, ix->ids_state, ix->cur_norm_q};
-        ix->rows = (uint8_t*)ix->sh_rows;
-        ix->pitch = (size_t)kpad * 2;
-        ix->store = B200_STORE_BF16;
-        ix->metric = B200_METRIC_IP;
-        ix->d = dv;
-        ix->d_pad = kpad;
-        ix->lpr = pick_lpr((size_t)kpad * 2 / 16);
-        ix->ids_state = 0;
-        ix->cur_norm_q = false;
+        // the scan kernel over the shadow: a view with bf16 rows of kpad columns, inner product, row positions as ids
+        const ScanView shadow{(const uint8_t*)ix->sh_rows, (size_t)kpad * 2, B200_STORE_BF16, B200_METRIC_IP, dv, kpad,
+                              pick_lpr((size_t)kpad * 2 / 16), nullptr, false};
         ScanPlan pl;
-        CKI(plan_scan(ix, 1, kp, false, &pl));
-        CKI(launch_scan(ix, pl, q_scan, 1, kp, Dp, Ip, nullptr, st));
+        CKI(plan_scan(ix, 1, kp, false, &pl, &shadow));
+        CKI(launch_scan(ix, pl, q_scan, 1, kp, Dp, Ip, nullptr, st, &shadow));
     }
     prefilter_lists_kernel<<<1, 256, 0, st>>>(Dp, Ip, kp, q_exact, ix->d, ix->d, cand, count, theta, qn2);
     ++ix->launches;

@@ -438,6 +438,223 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
 }
 
+// ---- K3 for small batches: rows as the M operand, queries resident ---------------------------------------------
+// With at most a few hundred queries the 256 x 256 kernel above is bound by operand traffic, not by the tensor pipe:
+// every 256-row tile re-fetches the whole query tile from L2 (as many bytes as the rows themselves), so a sweep of
+// the 15 GB shadow moves 30 GB from L2 into shared memory and takes 3.4-4.1 ms where HBM would allow 2.1.  This
+// form swaps the roles: the database rows are the M operand (256 rows per CTA pair, streamed by TMA through a
+// ring), the queries are the N operand (N = nq rounded up to 16, N <= 256 while N/2 x kpad bf16 fit next to the
+// ring) and are loaded into shared memory ONCE per CTA — the only stream is the shadow itself.  One
+// tcgen05.mma.cta_group::2 (M = 256, N, K = 16) per 32 bytes of K; accumulators [row lane, query column] in TMEM,
+// double buffered.  Epilogue: a thread owns one database row and compares its N scores with the queries' thresholds
+// (32 at a time from shared memory); the per-(query, 32-row group) maxima of the threshold pass are warp
+// reductions (redux.sync on the ordered-integer image).  Same candidate lists, same re-rank, same certificate.
+#define G3T_THREADS 192
+#define G3T_A_BYTES (128 * G3_BLOCK_K * 2)  // one CTA's half of a 256-row tile, one K block: 16 KB
+
+struct GemmRowsParams {
+    uint32_t nq;            // real queries
+    uint32_t n_cols;        // N: queries padded to a multiple of 16 (<= 256)
+    uint64_t n;             // database rows
+    uint32_t k_blocks;      // kpad / 64
+    uint32_t tile_first, tile_stride, tile_count;          // database tiles of this pass (as GemmParams)
+    uint32_t src_tile_first, src_tile_stride;              // where they sit behind tm_db
+    uint32_t stages;        // ring stages (host: what fits next to the resident queries)
+    int mode;
+    const float* theta;
+    unsigned int* cand_count;
+    uint32_t* cand_rows;
+    uint32_t cand_cap;
+    float* tilemax;         // [nq, tile_count * 8]
+    const uint32_t* row_mask;
+};
+
+template <int MODE, bool MASKED>
+__global__ void __launch_bounds__(G3T_THREADS, 1)
+gemm_rows_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_db,
+                      const GemmRowsParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t half_cols = p.n_cols / 2;                      // query rows this CTA holds
+    const uint32_t qblock_bytes = half_cols * G3_BLOCK_K * 2;     // one K block of them (multiple of 1024)
+    const uint32_t q_bytes = p.k_blocks * qblock_bytes;
+    const uint32_t ring_off = q_bytes;
+    const uint32_t bar_off = ring_off + p.stages * G3T_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + bar_off);
+    // bars[0..S): full, [S..2S): empty, [2S..2S+2): tmem_full, [2S+2..2S+4): tmem_empty, [2S+4]: queries resident
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 5);
+    float* s_theta = reinterpret_cast<float*>(bars + 2 * p.stages + 6);  // [n_cols rounded up to 32], +inf past nq
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    const uint32_t S = p.stages;
+    auto full_bar = [&](uint32_t s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar_base + 8u * (S + s); };
+    auto tfull_bar = [&](uint32_t b) { return bar_base + 8u * (2 * S + b); };
+    auto tempty_bar = [&](uint32_t b) { return bar_base + 8u * (2 * S + 2 + b); };
+    const uint32_t qres_bar = bar_base + 8u * (2 * S + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t group_id = blockIdx.x / 2, groups = gridDim.x / 2;
+    // two accumulator buffers of a power-of-two number of columns >= N and >= 32 (the epilogue reads 32 columns at a time)
+    const uint32_t tmem_cols = p.n_cols <= 32 ? 64u : (p.n_cols <= 64 ? 128u : (p.n_cols <= 128 ? 256u : 512u));
+    const uint32_t acc_stride = tmem_cols / 2;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_db);
+        for (uint32_t s = 0; s < S; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (uint32_t b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 8);  // four epilogue warps of each CTA of the pair
+        }
+        mbar_init(qres_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tc_alloc_cg<2>(smem_u32(tmem_slot), tmem_cols);
+    if (MODE == G3_MODE_EMIT)
+        for (uint32_t j = threadIdx.x; j < ((p.n_cols + 31u) & ~31u); j += blockDim.x) s_theta[j] = j < p.nq ? p.theta[j] : INFINITY;
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            // the queries, once: K block kb of this CTA's half of the query rows -> smem [kb]
+            if (leader) mbar_arrive_expect_tx(qres_bar, q_bytes * 2);
+            const uint32_t lead_q = mapa_shared(qres_bar, 0);
+            for (uint32_t kb = 0; kb < p.k_blocks; ++kb)
+                tma_load_2d_cg2(smem_base + kb * qblock_bytes, &tm_q, (int)(kb * G3_BLOCK_K), (int)(rank * half_cols), lead_q);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = group_id; t < p.tile_count; t += groups) {
+                const uint32_t src_tile = p.src_tile_first + t * p.src_tile_stride;
+                for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    if (leader) mbar_arrive_expect_tx(full_bar(stage), G3T_A_BYTES * 2);
+                    const uint32_t lead_bar = mapa_shared(full_bar(stage), 0);
+                    tma_load_2d_cg2(smem_base + ring_off + stage * G3T_A_BYTES, &tm_db, (int)(kb * G3_BLOCK_K),
+                                    (int)(src_tile * G3_BLOCK_N + rank * 128u), lead_bar);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA) =====
+        if (leader) {
+            const uint32_t idesc = umma_idesc_bf16(256, p.n_cols);
+            mbar_wait(qres_bar, 0);
+            tc_fence_after();
+            uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0;
+            for (uint32_t t = group_id; t < p.tile_count; t += groups) {
+                mbar_wait(tempty_bar(abuf), aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + abuf * acc_stride;
+                for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t adesc = umma_desc_k_sw128(smem_base + ring_off + stage * G3T_A_BYTES);
+                        const uint64_t bdesc = umma_desc_k_sw128(smem_base + kb * qblock_bytes);
+#pragma unroll
+                        for (uint32_t k = 0; k < G3_BLOCK_K / G3_UMMA_K; ++k)
+                            tc_mma_f16_cg<2>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_commit_cg<2>(empty_bar(stage));
+                        if (kb + 1 == p.k_blocks) tc_commit_cg<2>(tfull_bar(abuf));
+                    }
+                    __syncwarp();
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (++abuf == 2) {
+                    abuf = 0;
+                    aphase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: one database row per thread =====
+        const uint32_t quarter = (uint32_t)warp & 3u;
+        const uint32_t tempty_lead0 = mapa_shared(tempty_bar(0), 0);
+        const uint32_t groups32 = (p.n_cols + 31) / 32;
+        uint32_t abuf = 0, aphase = 0;
+        for (uint32_t t = group_id; t < p.tile_count; t += groups) {
+            const uint32_t ntile = p.tile_first + t * p.tile_stride;
+            const uint64_t row = (uint64_t)ntile * G3_BLOCK_N + rank * 128u + quarter * 32u + (uint32_t)lane;
+            bool live = row < p.n;
+            if (MASKED && live) live = (__ldg(p.row_mask + (row >> 5)) >> (row & 31)) & 1u;
+            mbar_wait(tfull_bar(abuf), aphase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((quarter * 32u) << 16) + abuf * acc_stride;
+            for (uint32_t g = 0; g < groups32; ++g) {
+                uint32_t v[32];
+                tc_ld_32x32b_x32(taddr0 + g * 32u, v);
+                tc_wait_ld_for(v);
+                const uint32_t c0 = g * 32u;
+                if (MODE == G3_MODE_TILEMAX) {
+                    // per query column: the maximum over this warp's 32 rows = one 32-row group of the tile
+                    float keep = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __uint_as_float(v[j]);
+                        const uint32_t o = (live && sc == sc) ? b200_ord_f32(sc) : 0u;  // NaN scores never count
+                        const uint32_t mx = __reduce_max_sync(B200_FULL_MASK, o);
+                        if (lane == j) keep = mx ? b200_unord_f32(mx) : -INFINITY;
+                    }
+                    const uint32_t qidx = c0 + (uint32_t)lane;
+                    if (qidx < p.nq) p.tilemax[((size_t)qidx * p.tile_count + t) * 8 + rank * 4u + quarter] = keep;
+                } else {
+                    if (live) {
+                        uint32_t hit = 0;
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 th = *reinterpret_cast<const float4*>(s_theta + c0 + 4 * j4);
+                            hit |= (__uint_as_float(v[4 * j4 + 0]) > th.x ? 1u : 0u) << (4 * j4 + 0);
+                            hit |= (__uint_as_float(v[4 * j4 + 1]) > th.y ? 1u : 0u) << (4 * j4 + 1);
+                            hit |= (__uint_as_float(v[4 * j4 + 2]) > th.z ? 1u : 0u) << (4 * j4 + 2);
+                            hit |= (__uint_as_float(v[4 * j4 + 3]) > th.w ? 1u : 0u) << (4 * j4 + 3);
+                        }
+                        while (hit) {  // rare
+                            const int j = __ffs(hit) - 1;
+                            hit &= hit - 1;
+                            const uint32_t qidx = c0 + (uint32_t)j;  // < nq: padded columns carry theta = +inf
+                            const unsigned pos = atomicAdd(p.cand_count + qidx, 1u);
+                            if (pos < p.cand_cap) p.cand_rows[(size_t)qidx * p.cand_cap + pos] = (uint32_t)row;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_lead0 + 8u * abuf);
+            if (++abuf == 2) {
+                abuf = 0;
+                aphase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tc_dealloc_cg<2>(tmem_base, tmem_cols);
+    }
+}
+
 // ---- shadow copies --------------------------------------------------------------------------------
 // fp32 rows (pitch bytes) -> bf16 K-major rows of kpad elements (zero padded) + fp32 squared norms
 // + a running maximum of the row norm (for the certificate's error bound).
