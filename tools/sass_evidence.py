@@ -34,7 +34,7 @@ def main():
         counts = {fam: sum(1 for l in body if re.search(r"\b" + fam, l)) for fam, _ in FAMILIES}
         if not any(counts[f] for f in ("UTCHMMA", "LDTM", "UTMALDG", "UBLKCP")):
             continue
-        key = "scan" if "scan_topk" in fn else "gemm" if "gemm_topk" in fn else "other"
+        key = "scan" if "scan_topk" in fn else "gemm" if ("gemm_topk" in fn or "gemm_rows_topk" in fn) else "other"
         txt = [f"== {pretty.get(fn, fn)[:200]}", f"   mangled {fn[:160]}", f"   registers {regs.get(fn, '?')}, SASS instructions {len(body)}",
                "   " + ", ".join(f"{fam} x{c}" for fam, c in counts.items() if c)]
         shown = set()
