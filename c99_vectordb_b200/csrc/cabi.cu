@@ -2140,8 +2140,17 @@ static int search_scan_block(b200_index* ix, const float* q_dev, int64_t nq, int
     return 0;
 }
 
+// exact_only: the scan / full-ranking paths only (what the row-sharded batch protocol falls back to)
+static int search_dev_impl(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev, int64_t* I_dev, void* stream,
+                           bool exact_only);
+
 extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev,
                                      int64_t* I_dev, void* stream) {
+    return search_dev_impl(ix, q_dev, nq, k, D_dev, I_dev, stream, false);
+}
+
+static int search_dev_impl(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, float* D_dev, int64_t* I_dev, void* stream,
+                           bool exact_only) {
     if (!ix) return fail("null index");
     if (nq < 0) return fail("negative nq");
     if (k <= 0) return fail("k must be positive, got %lld", (long long)k);
@@ -2163,7 +2172,7 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
         return 0;
     }
     const bool fullrank = k >= ix->opt_fullrank_min_k || k > B200_FUSED_K_MAX;
-    const bool use_gemm = !fullrank && !ix->xchg_active && gemm_eligible(ix, nq, k) && ix->sh_failed_rows != ix->ntotal;
+    const bool use_gemm = !exact_only && !fullrank && !ix->xchg_active && gemm_eligible(ix, nq, k) && ix->sh_failed_rows != ix->ntotal;
     struct NormGuard {  // the scan launches of THIS search normalise their queries while staging them
         b200_index* ix;
         ~NormGuard() { ix->cur_norm_q = false; }
@@ -2183,7 +2192,7 @@ extern "C" int b200_index_search_dev(b200_index* ix, const float* q_dev, int64_t
     }
     ix->stat_gemm_used = 0;
     ix->stat_prefilter_used = 0;
-    if (!fullrank && !use_gemm && nq == 1 && ix->opt_prefilter) {
+    if (!exact_only && !fullrank && !use_gemm && nq == 1 && ix->opt_prefilter) {
         const int rc = search_prefilter(ix, q_dev, k, D_dev, I_dev, st);
         if (rc != 2) return rc;
     }
@@ -2602,8 +2611,8 @@ extern "C" int b200_normalize_rows(float* x_host, int64_t n, int d, int device) 
 // fp32 scores of this shard's best candidates (best-first, padded) and in bound_dev[nq] the score no row outside
 // the list can beat; everything is enqueued on `stream`, nothing is read back.  Shards where the tensor-core path
 // does not apply (few rows, k > 256, no room for the shadow, a filter) answer with their exact top k from the scan
-// kernel and a bound that excludes nothing.  widen != 0 = second attempt for queries the merged certificate
-// rejected (3x more candidates).
+// kernel and a bound that excludes nothing.  widen: 0 = first attempt, 1 = second attempt for queries the merged
+// certificate rejected (3x more candidates), 2 = exact scan only (last resort; bound excludes nothing).
 extern "C" int b200_index_search_shard_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k, int world, int widen,
                                            float* D_dev, int64_t* I_dev, float* bound_dev, void* stream) {
     if (!ix) return fail("null index");
@@ -2616,8 +2625,9 @@ extern "C" int b200_index_search_shard_dev(b200_index* ix, const float* q_dev, i
     cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
     const bool fullrank = k >= ix->opt_fullrank_min_k || k > B200_FUSED_K_MAX;
     // at least 2 queries' worth of tensor work even when gemm_min_nq is lower; the caller decides what a batch is
-    const bool use_gemm = !fullrank && !ix->xchg_active && ix->ntotal > 0 && gemm_eligible(ix, std::max<int64_t>(nq, ix->opt_gemm_min_nq), k) &&
-                          ix->sh_failed_rows != ix->ntotal && ix->cur_mask == nullptr;
+    const bool use_gemm = widen != 2 && !fullrank && !ix->xchg_active && ix->ntotal > 0 &&
+                          gemm_eligible(ix, std::max<int64_t>(nq, ix->opt_gemm_min_nq), k) && ix->sh_failed_rows != ix->ntotal &&
+                          ix->cur_mask == nullptr;
     if (use_gemm) {
         CKI(order_after_previous_stream(ix, st));
         const float* q_raw = q_dev;
@@ -2635,7 +2645,7 @@ extern "C" int b200_index_search_shard_dev(b200_index* ix, const float* q_dev, i
         for (int64_t q0 = 0; q0 < nq && rc == 0; q0 += qblock) {
             const int64_t nb = std::min<int64_t>(qblock, nq - q0);
             rc = search_gemm(ix, q_dev + (size_t)q0 * ix->d, nb, k, D_dev + (size_t)q0 * k, I_dev + (size_t)q0 * k, st,
-                             widen ? 1 : 0, bound_dev + q0, world);
+                             widen == 1 ? 1 : 0, bound_dev + q0, world);
             if (rc == 2 && q0 != 0) return fail("the bf16 shadow disappeared between two blocks of one batch");
         }
         if (rc != 2) return rc;
@@ -2646,11 +2656,7 @@ extern "C" int b200_index_search_shard_dev(b200_index* ix, const float* q_dev, i
     if (ix->metric == B200_METRIC_IP) fill_neutral_bound_kernel<0><<<blocks, 256, 0, st>>>(bound_dev, nq);
     else fill_neutral_bound_kernel<1><<<blocks, 256, 0, st>>>(bound_dev, nq);
     CK(cudaGetLastError());
-    const int64_t keep_min = ix->opt_gemm_min_nq;
-    ix->opt_gemm_min_nq = 0;  // the exact paths only (scan / full ranking)
-    int rc = b200_index_search_dev(ix, q_dev, nq, k, D_dev, I_dev, stream);
-    ix->opt_gemm_min_nq = keep_min;
-    return rc;
+    return search_dev_impl(ix, q_dev, nq, k, D_dev, I_dev, stream, /*exact_only=*/true);
 }
 
 // K4 + certificate of a row-sharded batch: merges the G shard lists like b200_merge_topk_dev, then marks the queries

@@ -235,7 +235,8 @@ class ShardedIndexFlat:
         aim at 1/world of the candidates (b200_index_search_shard_dev: bf16 GEMM + fused emit + exact re-rank of ITS
         rows only, nothing read back), the lists and per-query exclusion bounds travel in ONE all-gather, and the
         certificate is taken after the merge: a query is done when its merged k-th entry strictly beats every shard's
-        bound.  The rest (identical on every rank, so no agreement step) is searched again, widened, then exactly."""
+        bound.  The rest (identical on every rank, so no agreement step) is searched again: widen = 1 collects 3x the
+        candidates, widen = 2 runs the exact scan on every shard (bounds that exclude nothing: always certified)."""
         import torch
         import torch.distributed as dist
 
@@ -288,31 +289,15 @@ class ShardedIndexFlat:
             if cuda:  # the pass brackets of the first attempt, before a retry overwrites them
                 base = self.local.index
                 self.last_batch_stats = {s: base.get_option("stat_gemm_" + s) for s in ("used", "pass1_us", "pass2_us", "rerank_us")}
-        if bad_count:
+        if bad_count and widen < 2:  # (after the exact scan there is nothing left to try: e.g. fewer valid rows than k)
             bad = torch.nonzero(unc, as_tuple=False).flatten()
             q_bad = q.index_select(0, bad).contiguous()
-            if widen == 0 and bad_count >= 2:
-                D_bad, I_bad = self._search_batch(q_bad, k, widen=1)
-            else:
-                D_bad, I_bad = self._search_exact(q_bad, k)
+            # same protocol, widened (3x the candidates), then with the exact scan on every shard (bounds exclude nothing)
+            D_bad, I_bad = self._search_batch(q_bad, k, widen=widen + 1)
             D, I = D.clone(), I.clone()  # the retry may have reused the cached buffers of this shape
             D.index_copy_(0, bad, D_bad)
             I.index_copy_(0, bad, I_bad)
         return D, I
-
-    def _search_exact(self, q, k: int):
-        """Exact scan on every shard (no tensor-core shortcut) + gather + merge: the last resort for queries whose
-        certificate failed twice."""
-        base = getattr(self.local, "index", self.local)
-        if self.device.type != "cuda":
-            return self._search_gather(q, k)
-        keep = base.get_option("gemm_min_nq")
-        base.set_option("gemm_min_nq", 0)
-        try:
-            D, I = self._search_gather(q, k)
-            return D.clone(), I.clone()
-        finally:
-            base.set_option("gemm_min_nq", keep)
 
     def search(self, x: np.ndarray, k: int):
         """Host query -> host result (every rank passes the same query and gets the same answer).

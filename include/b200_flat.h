@@ -247,7 +247,8 @@ int b200_merge_topk_dev(int metric, int G, int64_t nq, int64_t k, const float* D
  * row outside the list can beat; thresholds aim at 1/world of the candidates a single index would collect, so the
  * exact re-rank shrinks with the shard.  Everything is enqueued on `stream`; nothing is read back.  Shards the
  * tensor-core path does not serve (few rows, k > 256, no room for the bf16 shadow) answer with their exact top k
- * and a bound that excludes nothing.  widen != 0: second attempt with 3x more candidates.
+ * and a bound that excludes nothing.  widen: 0 = first attempt, 1 = second attempt with 3x more candidates, 2 = exact scan
+ * only (the last resort for queries whose certificate failed twice).
  * b200_merge_certify_dev merges the gathered shard lists (as b200_merge_topk_dev) and takes the certificate over
  * all shards: uncertified_dev[q] = 1 unless the merged k-th entry (k clipped to n_total) strictly beats every
  * shard's bound; *n_uncertified_dev counts them.  Uncertified queries are searched again by the caller (widened,

@@ -128,3 +128,19 @@ def test_shim_provides_every_faiss_symbol_memo_uses():
         for member in ("add_with_ids", "search", "ntotal", "id_map"):  # memo_cli.py:282,:292,:266,:268
             assert hasattr(cls, member), member
     assert issubclass(shim.IndexIDMap2, shim.IndexIDMap) and issubclass(shim.IndexHNSWFlat, shim.IndexFlat)
+
+
+def test_argument_checks_need_no_device():
+    """Entry points reject malformed calls with a status and a message before anything touches the device."""
+    L = _cabi.load()
+    null = C.c_void_p()
+    buf = (C.c_float * 4)()
+    assert L.b200_index_search_shard_dev(null, buf, 1, 10, 2, 0, buf, buf, buf, None) != 0
+    assert b"null index" in L.b200_last_error()
+    assert L.b200_merge_certify_dev(0, 2, 1, 10, 100, buf, buf, 0, 0, None, 0, buf, buf, None, None, None) != 0
+    assert b"null buffer" in L.b200_last_error()
+    added = C.c_int64(-1)
+    assert L.b200_index_add_texts(null, b"abc", None, 1, None, 0, 1, 1, 1, C.byref(added)) != 0
+    assert b"null index" in L.b200_last_error()
+    assert L.b200_index_search_dev(null, buf, 1, 10, buf, buf, None) != 0
+    assert L.b200_merge_topk_dev(7, 0, 1, 1, buf, buf, 0, 0, buf, buf, None) != 0

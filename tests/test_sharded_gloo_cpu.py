@@ -57,6 +57,9 @@ class ApproxLocalIndex(OracleLocalIndex):
         B = np.full(nq, -np.inf if self.metric == 0 else np.inf, np.float32)
         if n == 0:
             return D, I, B
+        if widen >= 2:  # the exact scan: this shard's true top k, a bound that excludes nothing
+            D, I = oracle.search(self.metric, self.rows, q, k, ids=self.ids)
+            return D, I, B
         rng = np.random.default_rng(1234 + n + widen)
         for i in range(nq):
             exact = (self.rows @ q[i]) if self.metric == 0 else ((self.rows - q[i]) ** 2).sum(axis=1)
@@ -73,6 +76,8 @@ class ApproxLocalIndex(OracleLocalIndex):
                 B[i] = theta - self.EPS
             Dc, Ic = oracle.search(self.metric, self.rows[cand], q[i:i + 1], k, ids=self.ids[cand])
             D[i], I[i] = Dc[0], Ic[0]
+        if widen == 1:  # an overflowed candidate list proves nothing: this query must reach the exact stage
+            B[0] = np.inf if self.metric == 0 else -np.inf
         return D, I, B
 
 
@@ -111,6 +116,7 @@ def test_sharded_batch_certificate_after_merge(tmp_path, world, metric, n, k, nq
     if n > 1000:
         assert 0 < unc, "the small candidate budget was meant to leave some queries uncertified"
         assert len(calls[0]) >= 2 and calls[0][1].tolist() == [unc, 1]
+        assert len(calls[0]) == 3 and calls[0][2].tolist() == [1, 2], "the query whose widened list 'overflowed' goes to the exact scan"
 
 
 def _free_port():
