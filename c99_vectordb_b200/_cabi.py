@@ -71,6 +71,7 @@ SIGNATURES = [
     ("b200_index_rows_dev", C.c_int, [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     ("b200_normalize_rows", C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int]),
     ("b200_merge_topk_dev", C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("b200_index_search_exchange", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     ("b200_index_search_shard_dev", C.c_int, [_h, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("b200_merge_certify_dev", C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

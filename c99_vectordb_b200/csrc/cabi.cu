@@ -113,6 +113,7 @@ struct b200_index {
     int64_t opt_gemm_min_rows = 4096, opt_gemm_min_nq = 2, opt_gemm_emit_factor = 8, opt_gemm_chunk_tiles = 0, opt_gemm_sample_tiles = 1024, opt_gemm_cta_group = 2,
             opt_gemm_shadow_max_rows = 0,  // > 0: keep at most this many rows of the bf16 shadow resident (streamed beyond; tests)
             opt_prefilter = 0,             // 1: single queries rank the bf16 shadow first (half the bytes), then re-rank exactly
+            opt_direct_results = 1,        // host API: small results are written straight into pinned host memory by the kernels
             opt_gemm_rows_form = 1;        // small batches: rows as the M operand, queries resident in shared memory (0: always the 256 x 256 form)
     // read-only statistics of the last batched (K3) search
     int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
@@ -408,6 +409,7 @@ static const OptName kOpts[] = {
     {"gemm_shadow_max_rows", &b200_index::opt_gemm_shadow_max_rows},
     {"prefilter", &b200_index::opt_prefilter},
     {"gemm_rows_form", &b200_index::opt_gemm_rows_form},
+    {"host_direct_results", &b200_index::opt_direct_results},
     {"stat_gemm_rows_form", &b200_index::stat_gemm_rows_form},
     {"stat_prefilter_used", &b200_index::stat_prefilter_used},
     {"stat_prefilter_fallbacks", &b200_index::stat_prefilter_fallbacks},
@@ -2248,8 +2250,15 @@ static int search_dev_impl(b200_index* ix, const float* q_dev, int64_t nq, int64
     return 0;
 }
 
+static int search_host_impl(b200_index* ix, const float* q_host, int64_t nq, int64_t k, float* D_host, int64_t* I_host, bool exchange);
+
 extern "C" int b200_index_search(b200_index* ix, const float* q_host, int64_t nq, int64_t k, float* D_host,
                                  int64_t* I_host) {
+    return search_host_impl(ix, q_host, nq, k, D_host, I_host, false);
+}
+
+// exchange: the fused multi-GPU form (b200_index_search_exchange_dev) instead of the local search
+static int search_host_impl(b200_index* ix, const float* q_host, int64_t nq, int64_t k, float* D_host, int64_t* I_host, bool exchange) {
     if (!ix) return fail("null index");
     if (nq < 0) return fail("negative nq");
     if (k <= 0) return fail("k must be positive, got %lld", (long long)k);
@@ -2257,6 +2266,9 @@ extern "C" int b200_index_search(b200_index* ix, const float* q_host, int64_t nq
     if (!q_host || !D_host || !I_host) return fail("null buffer");
     CKI(use_device(ix));
     cudaStream_t st = ix->stream;
+    auto search_any = [&](const float* qd, float* Dd, int64_t* Id) -> int {
+        return exchange ? b200_index_search_exchange_dev(ix, qd, nq, k, Dd, Id, st) : b200_index_search_dev(ix, qd, nq, k, Dd, Id, st);
+    };
     const size_t qn = (size_t)nq * ix->d, on = (size_t)nq * (size_t)k;
     if (ix->q_cap < qn || ix->out_cap < on) CK(cudaStreamSynchronize(st));
     CKI(grow(&ix->q_dev, &ix->q_cap, qn));
@@ -2288,9 +2300,15 @@ extern "C" int b200_index_search(b200_index* ix, const float* q_host, int64_t nq
         float* pq = (float*)(base + on * 12);
         memcpy(pq, q_host, qn * 4);
         CK(cudaMemcpyAsync(ix->q_dev, pq, qn * 4, cudaMemcpyHostToDevice, st));
-        CKI(b200_index_search_dev(ix, ix->q_dev, nq, k, ix->D_dev, ix->I_dev, st));
-        CK(cudaMemcpyAsync(pD, ix->D_dev, on * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(pI, ix->I_dev, on * 8, cudaMemcpyDeviceToHost, st));
+        if (on * 12 <= 4096 && ix->opt_direct_results) {
+            // a handful of results (the latency path): the kernels write them straight into the pinned buffer, which is
+            // device-addressable under unified addressing — no device->host copies after the search
+            CKI(search_any(ix->q_dev, pD, pI));
+        } else {
+            CKI(search_any(ix->q_dev, ix->D_dev, ix->I_dev));
+            CK(cudaMemcpyAsync(pD, ix->D_dev, on * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(pI, ix->I_dev, on * 8, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaStreamSynchronize(st));
         memcpy(D_host, pD, on * 4);
         memcpy(I_host, pI, on * 8);
@@ -2306,7 +2324,7 @@ extern "C" int b200_index_search(b200_index* ix, const float* q_host, int64_t nq
             CKI(upload_staged(ix, qs, qn * 4, (uint8_t*)ix->q_dev, false, 4, [](uint8_t*, size_t, size_t) { return 0; }));
         else
             CK(cudaMemcpyAsync(ix->q_dev, q_host, qn * 4, cudaMemcpyHostToDevice, st));
-        CKI(b200_index_search_dev(ix, ix->q_dev, nq, k, ix->D_dev, ix->I_dev, st));
+        CKI(search_any(ix->q_dev, ix->D_dev, ix->I_dev));
         if (staged) {
             CKI(download_staged(ix, (const uint8_t*)ix->D_dev, on * 4, (uint8_t*)D_host, st));
             CKI(download_staged(ix, (const uint8_t*)ix->I_dev, on * 8, (uint8_t*)I_host, st));
@@ -2489,6 +2507,16 @@ extern "C" int b200_index_search_exchange_dev(b200_index* ix, const float* q_dev
 
 // 0 = every fused exchange so far completed; 1 = a peer did not deliver in time (the affected search returned
 // padding only).  Read it after synchronising the stream the search ran on.
+// host query -> host result through the fused exchange, on the handle's own stream (one call = staging copy, H2D, the
+// kernel, results written straight into pinned host memory, one synchronisation, the exchange status check)
+extern "C" int b200_index_search_exchange(b200_index* ix, const float* q_host, int64_t nq, int64_t k, float* D_host, int64_t* I_host) {
+    int rc = search_host_impl(ix, q_host, nq, k, D_host, I_host, true);
+    if (rc) return rc;
+    if (ix->xchg_status_host && *ix->xchg_status_host)
+        return fail("fused exchange: a peer GPU did not deliver its results in time; the search returned no results");
+    return 0;
+}
+
 extern "C" int b200_index_exchange_status(b200_index* ix) {
     if (!ix) return -1;
     return ix->xchg_status_host ? *ix->xchg_status_host : 0;

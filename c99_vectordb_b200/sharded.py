@@ -309,6 +309,15 @@ class ShardedIndexFlat:
         if self.device.type != "cuda":
             D, I = self.search_device(torch.from_numpy(x), k)
             return D.numpy().copy(), I.numpy().copy()
+        if self._fused_ok(x.shape[0], int(k)):
+            # latency path: ONE C call — pinned staging, H2D, the fused kernel (its last CTA writes the merged result
+            # straight into pinned host memory), one synchronisation, the exchange status check.  It runs on the index's
+            # own stream; the library orders that stream behind the one the handle used last.
+            D = np.empty((x.shape[0], int(k)), dtype=np.float32)
+            I = np.empty((x.shape[0], int(k)), dtype=np.int64)
+            _cabi.check(_cabi.load().b200_index_search_exchange(self.local.index._h, x.ctypes.data, x.shape[0], int(k),
+                                                                D.ctypes.data, I.ctypes.data))
+            return D, I
         key = (x.shape[0], int(k))
         st = self._host_stage.get(key)
         if st is None:

@@ -203,6 +203,9 @@ size_t b200_exchange_slot_bytes(void);
 int b200_index_set_exchange(b200_index* ix, int world, int rank, void* const* peer_bufs);
 int b200_index_search_exchange_dev(b200_index* ix, const float* q_dev, int64_t nq, int64_t k,
                                    float* D_dev, int64_t* I_dev, void* stream);
+/* host query -> host result through the fused exchange on the handle's own stream (collective: every rank calls it
+ * with the same query); fails when a peer did not deliver in time */
+int b200_index_search_exchange(b200_index* ix, const float* q_host, int64_t nq, int64_t k, float* D_host, int64_t* I_host);
 int b200_index_exchange_status(b200_index* ix);
 /* profiling aid: with option scan_phase_stamps = 1 every scan launch records per-CTA globaltimer stamps
  * (ns): out[cta*8 + j], j = 0 kernel entry, 1 queries staged, 2 scan done (warp 0), 3 CTA reduction
