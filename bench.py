@@ -497,6 +497,14 @@ def run_workload(env: Env, a, workload: str, steps: int, warmup: int, *, headlin
     sampler = ClockSampler(env.local_rank) if headline else None
     if sampler and rank == 0:
         sampler.start()
+    if nq > 1 and base.get_option("gemm_min_nq") > 0:
+        # warm-up of the batched path's RARE branches too: starved thresholds make certificates fail, so the widened
+        # second pass and the exact-scan fallback run once before anything is timed (CUDA loads a kernel on first use;
+        # a query set that needs a retry would otherwise pay hundreds of ms of one-time loading inside a timed step)
+        keep = base.get_option("gemm_emit_factor")
+        base.set_option("gemm_emit_factor", 2)
+        idx.search_device(q_all[0][: min(nq, 512)].contiguous(), k)
+        base.set_option("gemm_emit_factor", keep)
     for s in range(warmup):
         idx.search_device(q_all[s], k)
     env.barrier()
@@ -614,7 +622,8 @@ def run_workload(env: Env, a, workload: str, steps: int, warmup: int, *, headlin
                          "avg_launch_ms": launch_ms, "isolated_launch_ms": iso_p50 / scans_per_step, "peak_source": peak_src,
                          "whole_job_gbs": bytes_per_scan_total * scans_per_step / (total_ms / steps * 1e-3) / 1e9},
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12,
-                    "p50_ms": 1e3 * statistics.median(e2e_lat), "timing": "host wall clock around index.search(numpy)"},
+                    "p50_ms": 1e3 * statistics.median(e2e_lat), "max_ms": 1e3 * max(e2e_lat),
+                    "timing": "host wall clock around index.search(numpy)"},
             "gpu_launches": int(launches),
             "parity": parity,
         }

@@ -29,7 +29,7 @@ def make(n, d, nq, span, seed):
 
 
 @pytest.mark.parametrize("metric", [0, 1])
-@pytest.mark.parametrize("n,d,span", [(50_000, 32, 1), (30_000, 100, 2), (20_001, 384, 1), (9_000, 768, 3)])
+@pytest.mark.parametrize("n,d,span", [(30_000, 32, 1), (12_000, 100, 2), (9_001, 384, 1)])
 def test_scan_and_full_ranking(b200, metric, n, d, span):
     db, q = make(n, d, 3, span, n + d)
     ids = np.arange(n, dtype=np.int64) * 3 - 7
@@ -52,7 +52,7 @@ def test_scan_and_full_ranking(b200, metric, n, d, span):
 def test_tensor_core_forms_under_massive_ties(b200, metric, nq, rows_form):
     """Thousands of rows share the k-th score: the certificate cannot separate them and must hand over to the widened
     pass / the exact scan; whatever path answers, the tie rule decides."""
-    n, d, k = 120_000, 128, 10
+    n, d, k = 70_000, 128, 10
     db, q = make(n, d, nq, 1, 77 + nq)
     idx = b200.IndexFlat(d, metric)
     idx.add(db)
@@ -102,7 +102,7 @@ def test_row_shards_merge_with_the_global_tie_rule(b200, metric):
     from c99_vectordb_b200.sharded import shard_range
 
     L = _cabi.load()
-    n, d, k, nq, world = 90_000, 64, 20, 24, 3
+    n, d, k, nq, world = 60_000, 64, 20, 24, 3
     db, q = make(n, d, nq, 1, 11)
     ids = np.arange(n, dtype=np.int64)
     shards = []

@@ -73,7 +73,7 @@ def test_add_device_tensor(b200):
     np.testing.assert_array_equal(b200.vector_to_array(idx.id_map), ids.cpu().numpy())
 
 
-K3_CASES = int(os.environ.get("B200_RANDOM_K3_CASES", "24"))
+K3_CASES = int(os.environ.get("B200_RANDOM_K3_CASES", "16"))
 
 
 @pytest.mark.parametrize("seed", range(K3_CASES))
