@@ -57,8 +57,8 @@ def check_list(metric, D, I, n):
 CASES = [
     # BASELINE headline / config 2 database, config 3, config 4
     pytest.param(dict(n=10_000_000, d=768, metric=0, store="f32", normalize=False, halves=True, k3=True), id="10Mx768_ip_f32"),
-    pytest.param(dict(n=100_000_000, d=384, metric=1, store="f32", normalize=False, halves=False, k3=False), id="100Mx384_l2_f32"),
-    pytest.param(dict(n=10_000_000, d=1024, metric=0, store="bf16", normalize=True, halves=True, k3=False), id="10Mx1024_cos_bf16"),
+    pytest.param(dict(n=100_000_000, d=384, metric=1, store="f32", normalize=False, halves=False, k3=True), id="100Mx384_l2_f32"),
+    pytest.param(dict(n=10_000_000, d=1024, metric=0, store="bf16", normalize=True, halves=True, k3=True), id="10Mx1024_cos_bf16"),
 ]
 
 
