@@ -61,7 +61,9 @@ WORKLOADS[PREFILTER_WORKLOAD] = WORKLOADS["10Mx768_ip_f32_k10_nq1"]
 WORKLOAD_OPTIONS = {PREFILTER_WORKLOAD: {"prefilter": 1}}
 DEFAULT_WORKLOAD = "10Mx768_ip_f32_k10_nq1"
 # BASELINE.json configs 1-4, timed briefly next to the headline (the 10M x 768 database of config 2 is the headline's)
-OTHER_CONFIGS = ["1Mx768_cos_f32_k10_nq1", "10Mx768_ip_f32_k100_nq10000", "10Mx1024_cos_bf16_k10_nq1", "100Mx384_l2_f32_k10_nq1"]
+OTHER_CONFIGS = ["10kx384_ip_f32_k10_nq100", "1Mx768_cos_f32_k10_nq1", "10Mx768_ip_f32_k100_nq10000", "10Mx1024_cos_bf16_k10_nq1",
+                 "100Mx384_l2_f32_k10_nq1"]
+L2_BYTES = 126 * 1024 * 1024
 DB_SEED, Q_SEED = 1234, 5678
 METRIC_LABEL = {
     "10Mx768_ip_f32_k10_nq1": "QPS @k=10, 10Mx768 flat IP (single query)",
@@ -78,7 +80,19 @@ def workload_config(workload: str, world: int) -> dict:
     per = -(-n // world)
     return {"workload": workload, "rows": n, "d": d, "k": k, "nq": nq, "metric": "ip" if metric == 0 else "l2",
             "store": store, "normalize": normalize, "sharding": f"row-wise x{world}", "rows_per_gpu": per,
-            "l2_policy": "database >> 126 MB L2, distinct query per step; no flush needed"}
+            "l2_policy": l2_policy(workload, world)}
+
+
+def l2_policy(workload: str, world: int) -> str:
+    n, d, metric, store, normalize, k, nq = WORKLOADS[workload]
+    shard_bytes = -(-n // world) * d * (4 if store == "f32" else 2)
+    if shard_bytes > 4 * L2_BYTES:
+        return "database >> 126 MB L2, distinct query per step; no flush needed"
+    if shard_bytes > L2_BYTES:
+        return (f"database shard ({shard_bytes / 1e6:.0f} MB) > 126 MB L2 and streamed front to back every step (the front of the shard is evicted "
+                "before the next step reads it again); distinct query per step; no flush")
+    return (f"database shard ({shard_bytes / 1e6:.1f} MB) fits the 126 MB L2 and is not flushed between steps: a latency figure "
+            "(launch-bound), no bandwidth claim; distinct queries per step")
 
 
 def scan_passes(nq: int) -> int:
@@ -551,17 +565,16 @@ def run_workload(env: Env, a, workload: str, steps: int, warmup: int, *, headlin
     value = steps * nq / (total_ms * 1e-3)
 
     # ---- e2e: host query -> host result through the public API ----
+    # index.search(numpy) -> numpy: the C ABI host entry on one GPU, the sharded host entry otherwise
+    host_search = idx.local.search if world == 1 else idx.search
     for s in range(min(warmup, 3)):
-        idx.search(q_host[s], k)
+        host_search(q_host[s], k)  # the SAME call as the timed one (its pinned staging is sized on first use)
     env.barrier()
     e2e_lat = []
     t_start = time.perf_counter()
     for s in range(steps):
         t1 = time.perf_counter()
-        if world == 1:
-            D_h, I_h = idx.local.search(q_host[warmup + s], k)  # index.search(numpy) -> numpy (C ABI host entry)
-        else:
-            D_h, I_h = idx.search(q_host[warmup + s], k)
+        D_h, I_h = host_search(q_host[warmup + s], k)
         e2e_lat.append(time.perf_counter() - t1)
     env.barrier()
     e2e_total, = env.max_over_ranks([time.perf_counter() - t_start])
@@ -702,6 +715,11 @@ def main_b200(a):
                     keep = {k2: r[k2] for k2 in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "p50_ms", "dtype",
                                                  "roofline", "e2e", "gpu_launches", "parity", "prefilter") if k2 in r}
                     keep["workload"] = w
+                    keep["l2_policy"] = l2_policy(w, env.world)
+                    if w == "10kx384_ip_f32_k10_nq100" and not a.no_cpu:
+                        # BASELINE config 0 is the reference's own CPU-runnable case: the host does it in full
+                        cb0 = run_cpu(w, 5, 1, host_threads())
+                        keep["cpu_baseline"] = {k2: cb0[k2] for k2 in ("value", "unit", "cores", "kind", "sample", "extrapolated")}
                     for k2 in r:
                         if k2.startswith("recall_at_"):
                             keep[k2] = r[k2]

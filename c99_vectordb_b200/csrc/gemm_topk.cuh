@@ -207,6 +207,78 @@ __device__ __forceinline__ void tc_commit_cg(uint32_t bar) {
     }
 }
 
+// Warp-uniform issue.  Inside a divergent `if (lane == 0)` region ptxas has to move every operand of a tcgen05
+// instruction into uniform registers through an ELECT / R2UR waterfall (about 14 instructions and a loop per MMA —
+// measurable once an MMA takes 32 cycles).  Here every lane of the MMA warp runs the loop, the operands are computed
+// in the uniform datapath, and the instructions are predicated on one elected lane.
+__device__ __forceinline__ uint32_t elect_one_pred() {
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
+    return e;
+}
+// elected-lane forms of the TMA producer's instructions (the producer warp runs its loop warp-uniformly too)
+__device__ __forceinline__ void mbar_arrive_expect_tx_if(uint32_t elected, uint32_t bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "setp.ne.b32 e, %2, 0;\n\t"
+        "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+        ::"r"(bar), "r"(bytes), "r"(elected)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_if(uint32_t elected, uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "setp.ne.b32 e, %5, 0;\n\t"
+        "@e cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n\t}"
+        ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(bar), "r"(elected)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2_if(uint32_t elected, uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "setp.ne.b32 e, %5, 0;\n\t"
+        "@e cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+        ::"r"(dst_smem), "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(elected)
+        : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tc_mma_f16_cg_if(uint32_t elected, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    if (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred p, e;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "setp.ne.b32 e, %5, 0;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p, e;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "setp.ne.b32 e, %5, 0;\n\t"
+            "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected)
+            : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tc_commit_cg_if(uint32_t elected, uint32_t bar) {
+    if (CG == 1)
+        asm volatile(
+            "{\n\t.reg .pred e;\n\t"
+            "setp.ne.b32 e, %1, 0;\n\t"
+            "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+            ::"r"(bar), "r"(elected)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred e;\n\t"
+            "setp.ne.b32 e, %2, 0;\n\t"
+            "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+            ::"r"(bar), "h"((uint16_t)3), "r"(elected)
+            : "memory");
+}
+
 template <int CG>
 struct G3Cfg {
     static constexpr uint32_t kBRows = G3_BLOCK_N / CG;            // rows of the N tile staged by one CTA
@@ -272,7 +344,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
     if (warp == 0) {
         // ===== TMA producer (every CTA) =====
-        if (lane == 0) {
+        {
+            const uint32_t elected = elect_one_pred();
             uint32_t stage = 0, phase = 0;
             // CG == 2: completion bytes are credited to the LEADER's full barrier
             for (uint32_t u = group_id; u < units; u += groups) {
@@ -287,14 +360,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                         const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
                         const int kc = (int)(kb * G3_BLOCK_K);
                         if (CG == 1) {
-                            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                            tma_load_2d(a_dst, &tm_q, kc, (int)(mt * G3_BLOCK_M), full_bar(stage));
-                            tma_load_2d(a_dst + G3_A_BYTES, &tm_db, kc, (int)(ntile * G3_BLOCK_N), full_bar(stage));
+                            mbar_arrive_expect_tx_if(elected, full_bar(stage), Cfg::kStageBytes);
+                            tma_load_2d_if(elected, a_dst, &tm_q, kc, (int)(mt * G3_BLOCK_M), full_bar(stage));
+                            tma_load_2d_if(elected, a_dst + G3_A_BYTES, &tm_db, kc, (int)(ntile * G3_BLOCK_N), full_bar(stage));
                         } else {
-                            if (leader) mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes * 2);
+                            if (leader) mbar_arrive_expect_tx_if(elected, full_bar(stage), Cfg::kStageBytes * 2);
                             const uint32_t lead_bar = mapa_shared(full_bar(stage), 0);
-                            tma_load_2d_cg2(a_dst, &tm_q, kc, (int)(mt * G3_BLOCK_M), lead_bar);
-                            tma_load_2d_cg2(a_dst + G3_A_BYTES, &tm_db, kc, (int)(ntile * G3_BLOCK_N + rank * Cfg::kBRows), lead_bar);
+                            tma_load_2d_cg2_if(elected, a_dst, &tm_q, kc, (int)(mt * G3_BLOCK_M), lead_bar);
+                            tma_load_2d_cg2_if(elected, a_dst + G3_A_BYTES, &tm_db, kc, (int)(ntile * G3_BLOCK_N + rank * Cfg::kBRows), lead_bar);
                         }
                         if (++stage == Cfg::kStages) {
                             stage = 0;
@@ -308,6 +381,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         // ===== MMA issuer (the pair's leader only) =====
         if (leader) {
             const uint32_t idesc = umma_idesc_bf16(G3_BLOCK_M * CG, G3_BLOCK_N);
+            const uint32_t elected = elect_one_pred();
             uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0;
             for (uint32_t u = group_id; u < units; u += groups) {
                 const uint32_t chunk = u / m_groups;
@@ -320,19 +394,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
-                        if (lane == 0) {
-                            const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
-                            const uint64_t adesc = umma_desc_k_sw128(a_addr);
-                            const uint64_t bdesc = umma_desc_k_sw128(a_addr + G3_A_BYTES);
+                        const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+                        const uint64_t adesc = umma_desc_k_sw128(a_addr);
+                        const uint64_t bdesc = umma_desc_k_sw128(a_addr + G3_A_BYTES);
 #pragma unroll
-                            for (uint32_t k = 0; k < G3_BLOCK_K / G3_UMMA_K; ++k) {
-                                // advance 32 bytes (16 bf16) inside the swizzle atom: +2 in the >>4 encoded address
-                                tc_mma_f16_cg<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                            }
-                            tc_commit_cg<CG>(empty_bar(stage));  // smem slot free (in both CTAs) once these MMAs retire
-                            if (kb + 1 == p.k_blocks) tc_commit_cg<CG>(tfull_bar(abuf));  // accumulator complete
+                        for (uint32_t k = 0; k < G3_BLOCK_K / G3_UMMA_K; ++k) {
+                            // advance 32 bytes (16 bf16) inside the swizzle atom: +2 in the >>4 encoded address
+                            tc_mma_f16_cg_if<CG>(elected, d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
-                        __syncwarp();
+                        tc_commit_cg_if<CG>(elected, empty_bar(stage));  // smem slot free (in both CTAs) once these MMAs retire
+                        if (kb + 1 == p.k_blocks) tc_commit_cg_if<CG>(elected, tfull_bar(abuf));  // accumulator complete
                         if (++stage == Cfg::kStages) {
                             stage = 0;
                             phase ^= 1u;
@@ -527,21 +598,22 @@ gemm_rows_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        {
+            const uint32_t elected = elect_one_pred();
             // the queries, once: K block kb of this CTA's half of the query rows -> smem [kb]
-            if (leader) mbar_arrive_expect_tx(qres_bar, q_bytes * 2);
+            if (leader) mbar_arrive_expect_tx_if(elected, qres_bar, q_bytes * 2);
             const uint32_t lead_q = mapa_shared(qres_bar, 0);
             for (uint32_t kb = 0; kb < p.k_blocks; ++kb)
-                tma_load_2d_cg2(smem_base + kb * qblock_bytes, &tm_q, (int)(kb * G3_BLOCK_K), (int)(rank * half_cols), lead_q);
+                tma_load_2d_cg2_if(elected, smem_base + kb * qblock_bytes, &tm_q, (int)(kb * G3_BLOCK_K), (int)(rank * half_cols), lead_q);
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = group_id; t < p.tile_count; t += groups) {
                 const uint32_t src_tile = p.src_tile_first + t * p.src_tile_stride;
                 for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
-                    if (leader) mbar_arrive_expect_tx(full_bar(stage), G3T_A_BYTES * 2);
+                    if (leader) mbar_arrive_expect_tx_if(elected, full_bar(stage), G3T_A_BYTES * 2);
                     const uint32_t lead_bar = mapa_shared(full_bar(stage), 0);
-                    tma_load_2d_cg2(smem_base + ring_off + stage * G3T_A_BYTES, &tm_db, (int)(kb * G3_BLOCK_K),
-                                    (int)(src_tile * G3_BLOCK_N + rank * 128u), lead_bar);
+                    tma_load_2d_cg2_if(elected, smem_base + ring_off + stage * G3T_A_BYTES, &tm_db, (int)(kb * G3_BLOCK_K),
+                                       (int)(src_tile * G3_BLOCK_N + rank * 128u), lead_bar);
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1u;
@@ -553,6 +625,7 @@ gemm_rows_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
         // ===== MMA issuer (leader CTA) =====
         if (leader) {
             const uint32_t idesc = umma_idesc_bf16(256, p.n_cols);
+            const uint32_t elected = elect_one_pred();
             mbar_wait(qres_bar, 0);
             tc_fence_after();
             uint32_t stage = 0, phase = 0, abuf = 0, aphase = 0;
@@ -563,16 +636,13 @@ gemm_rows_topk_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_con
                 for (uint32_t kb = 0; kb < p.k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint64_t adesc = umma_desc_k_sw128(smem_base + ring_off + stage * G3T_A_BYTES);
-                        const uint64_t bdesc = umma_desc_k_sw128(smem_base + kb * qblock_bytes);
+                    const uint64_t adesc = umma_desc_k_sw128(smem_base + ring_off + stage * G3T_A_BYTES);
+                    const uint64_t bdesc = umma_desc_k_sw128(smem_base + kb * qblock_bytes);
 #pragma unroll
-                        for (uint32_t k = 0; k < G3_BLOCK_K / G3_UMMA_K; ++k)
-                            tc_mma_f16_cg<2>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                        tc_commit_cg<2>(empty_bar(stage));
-                        if (kb + 1 == p.k_blocks) tc_commit_cg<2>(tfull_bar(abuf));
-                    }
-                    __syncwarp();
+                    for (uint32_t k = 0; k < G3_BLOCK_K / G3_UMMA_K; ++k)
+                        tc_mma_f16_cg_if<2>(elected, d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit_cg_if<2>(elected, empty_bar(stage));
+                    if (kb + 1 == p.k_blocks) tc_commit_cg_if<2>(elected, tfull_bar(abuf));
                     if (++stage == S) {
                         stage = 0;
                         phase ^= 1u;
