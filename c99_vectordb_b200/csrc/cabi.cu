@@ -22,7 +22,6 @@
 #include "embed_dev.cuh"
 #include "fullrank.cuh"
 #include "gemm_topk.cuh"
-#include "gemm_ts.cuh"
 #include "merge.cuh"
 #include "rows.cuh"
 #include "scan_topk.cuh"
@@ -115,13 +114,12 @@ struct b200_index {
             opt_gemm_shadow_max_rows = 0,  // > 0: keep at most this many rows of the bf16 shadow resident (streamed beyond; tests)
             opt_prefilter = 0,             // 1: single queries rank the bf16 shadow first (half the bytes), then re-rank exactly
             opt_direct_results = 1,        // host API: small results are written straight into pinned host memory by the kernels
-            opt_gemm_rows_form = 1,        // small batches: rows as the M operand, queries resident in shared memory (0: always the 256 x 256 form)
-            opt_gemm_ts = 0;               // experiment (1): large batches, K <= 768, queries resident in tensor memory (gemm_ts.cuh) — slower than the smem-operand form, see profiles/r2_gemm_ts_experiment.jsonl
+            opt_gemm_rows_form = 1;        // small batches: rows as the M operand, queries resident in shared memory (0: always the 256 x 256 form)
     // read-only statistics of the last batched (K3) search
     int64_t stat_gemm_used = 0, stat_gemm_fallbacks = 0, stat_gemm_cand_total = 0, stat_gemm_pass1_us = 0,
             stat_gemm_pass2_us = 0, stat_gemm_rerank_us = 0, stat_gemm_scan_fallbacks = 0, stat_gemm_pre_us = 0,
             stat_gemm_host_us = 0, stat_gemm_streamed = 0, stat_prefilter_used = 0, stat_prefilter_fallbacks = 0,
-            stat_gemm_rows_form = 0, stat_gemm_ts = 0;
+            stat_gemm_rows_form = 0;
     // K3 state
     __nv_bfloat16* sh_rows = nullptr;  // bf16 shadow of the rows [ntotal, kpad]
     float* sh_norm2 = nullptr;
@@ -411,8 +409,6 @@ static const OptName kOpts[] = {
     {"gemm_shadow_max_rows", &b200_index::opt_gemm_shadow_max_rows},
     {"prefilter", &b200_index::opt_prefilter},
     {"gemm_rows_form", &b200_index::opt_gemm_rows_form},
-    {"gemm_ts", &b200_index::opt_gemm_ts},
-    {"stat_gemm_ts", &b200_index::stat_gemm_ts},
     {"host_direct_results", &b200_index::opt_direct_results},
     {"stat_gemm_rows_form", &b200_index::stat_gemm_rows_form},
     {"stat_prefilter_used", &b200_index::stat_prefilter_used},
@@ -1712,25 +1708,6 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     }
     const bool rows_form = rows_stages >= 4;
     ix->stat_gemm_rows_form = rows_form ? 1 : 0;
-    // Large batches whose K fits: the queries of a work unit stay in tensor memory (gemm_ts.cuh), only the rows stream.
-    // kpad / 2 columns of queries + two NT-column accumulators fill the 512 columns: NT = 128 up to K = 512, 64 up to 768.
-    const bool ts_form = cg == 2 && !rows_form && ix->opt_gemm_ts != 0 && kpad <= 768;
-    const uint32_t ts_nt = kpad <= 512 ? 128u : 64u;
-    uint32_t ts_kps = 1, ts_stages = 0;
-    size_t ts_smem = 0;
-    if (ts_form) {
-        const uint32_t kbs = (uint32_t)(kpad / G3_BLOCK_K), kb_bytes = G3S_KB_BYTES(ts_nt);
-        for (uint32_t c = 16384 / kb_bytes; c >= 1; --c)
-            if (kbs % c == 0) {
-                ts_kps = c;
-                break;
-            }
-        const size_t stage_bytes = (size_t)ts_kps * kb_bytes;
-        ts_stages = (uint32_t)std::min<size_t>(12, (ix->smem_optin - 2048) / stage_bytes);
-        ts_smem = 1024 + (size_t)ts_stages * stage_bytes + (2 * ts_stages + 6) * 8 + 64;
-        ts_smem = std::max<size_t>(ts_smem, (size_t)120 << 10);  // one CTA per SM: each allocates all of tensor memory
-    }
-    if (depth == 0) ix->stat_gemm_ts = ts_form ? 1 : 0;
     // ---- scratch ----
     const size_t qb_elems = (size_t)((m_tiles + 1) / 2 * 2) * G3_BLOCK_M * kpad;  // whole 256-query groups
     // sampled tiles: each contributes 8 group maxima; at most 8192 maxima per query are sorted
@@ -1782,21 +1759,6 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
         for (int b = 0; b < 2; ++b)
             CKI(make_tmap_bf16(&tm_half[b], ix->sh_rows + (size_t)b * C2 * kpad, (uint64_t)C2, (uint32_t)kpad, G3_BLOCK_N / cg));
     const bool masked = ix->cur_mask != nullptr;
-    CUtensorMap tm_db_ts, tm_half_ts[2];
-    if (ts_form) {
-        CKI(make_tmap_bf16(&tm_db_ts, ix->sh_rows, streamed ? (uint64_t)S : n, (uint32_t)kpad, ts_nt / 2));
-        if (streamed)
-            for (int b = 0; b < 2; ++b)
-                CKI(make_tmap_bf16(&tm_half_ts[b], ix->sh_rows + (size_t)b * C2 * kpad, (uint64_t)C2, (uint32_t)kpad, ts_nt / 2));
-    }
-    typedef void (*GemmTsFn)(const CUtensorMap, const GemmTsParams);
-    GemmTsFn tfns[2] = {
-        ts_nt == 128 ? (masked ? gemm_topk_ts_kernel<128, true, G3_MODE_TILEMAX> : gemm_topk_ts_kernel<128, false, G3_MODE_TILEMAX>)
-                     : (masked ? gemm_topk_ts_kernel<64, true, G3_MODE_TILEMAX> : gemm_topk_ts_kernel<64, false, G3_MODE_TILEMAX>),
-        ts_nt == 128 ? (masked ? gemm_topk_ts_kernel<128, true, G3_MODE_EMIT> : gemm_topk_ts_kernel<128, false, G3_MODE_EMIT>)
-                     : (masked ? gemm_topk_ts_kernel<64, true, G3_MODE_EMIT> : gemm_topk_ts_kernel<64, false, G3_MODE_EMIT>)};
-    if (ts_form)
-        for (GemmTsFn f : tfns) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts_smem));
     CUtensorMap tm_q_rows;
     if (rows_form) CKI(make_tmap_bf16(&tm_q_rows, ix->g_qb, (uint64_t)((m_tiles + 1) / 2 * 2) * G3_BLOCK_M, (uint32_t)kpad, n_cols / 2));
     typedef void (*GemmRowsFn)(const CUtensorMap, const CUtensorMap, const GemmRowsParams);
@@ -1813,33 +1775,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
                 : (masked ? gemm_topk_kernel<2, true, G3_MODE_EMIT> : gemm_topk_kernel<2, false, G3_MODE_EMIT>)};
     const size_t gsmem = cg == 1 ? G3Cfg<1>::kSmemBytes : G3Cfg<2>::kSmemBytes;
     for (GemmFn f : gfns) CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-    // half: -1 = the map over the whole (resident or packed) shadow, 0 / 1 = a chunk buffer of the streamed scratch
-    auto launch_gemm = [&](const GemmParams& g, const CUtensorMap& tm_rows, int half) -> int {
-        if (ts_form) {
-            GemmTsParams t;
-            memset(&t, 0, sizeof t);
-            t.g = g;
-            t.qb = reinterpret_cast<const uint32_t*>(ix->g_qb);
-            t.kps = ts_kps;
-            t.stages = ts_stages;
-            cudaLaunchConfig_t cfg;
-            memset(&cfg, 0, sizeof cfg);
-            cfg.gridDim = dim3((unsigned)(ix->num_sms / 2 * 2));
-            cfg.blockDim = dim3(G3S_THREADS);
-            cfg.dynamicSmemBytes = ts_smem;
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 2;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            CK(cudaLaunchKernelEx(&cfg, tfns[g.mode == G3_MODE_EMIT ? 1 : 0], half < 0 ? tm_db_ts : tm_half_ts[half], t));
-            ++ix->launches;
-            CK(cudaGetLastError());
-            return 0;
-        }
+    auto launch_gemm = [&](const GemmParams& g, const CUtensorMap& tm_rows) -> int {
         if (rows_form) {
             GemmRowsParams r;
             memset(&r, 0, sizeof r);
@@ -1931,7 +1867,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
         CK(cudaGetLastError());
         gp.src_tile_stride = 1;
     }
-    CKI(launch_gemm(gp, tm_db, -1));
+    CKI(launch_gemm(gp, tm_db));
     {
         // expected emissions per query = emit_factor * k.  The rank-th largest of the sampled
         // 32-row group maxima estimates the score quantile (sample rows / n) * that count; the rank
@@ -1953,7 +1889,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
     if (!streamed) {
         gp.tile_first = gp.src_tile_first = 0;
         gp.tile_count = NT;
-        CKI(launch_gemm(gp, tm_db, -1));
+        CKI(launch_gemm(gp, tm_db));
     } else {
         // streamed shadow: the fp32 rows are rounded chunk by chunk into the two halves of the scratch; the converter
         // runs on a second stream, so chunk c+1 is converted (HBM-bound) while the GEMM sweeps chunk c
@@ -1979,7 +1915,7 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
             gp.tile_first = (uint32_t)(r0 / G3_BLOCK_N);
             gp.src_tile_first = 0;
             gp.tile_count = (uint32_t)((rows_c + G3_BLOCK_N - 1) / G3_BLOCK_N);
-            CKI(launch_gemm(gp, tm_half[b], b));
+            CKI(launch_gemm(gp, tm_half[b]));
             CK(cudaEventRecord(ix->sh_ev[2 + b], st));
         }
     }

@@ -20,7 +20,8 @@
 //      are re-run through the exact scan kernel.
 //
 // Warp roles (6 warps): 0 = TMA producer, 1 = MMA issuer (+ TMEM allocator), 2..5 = epilogue
-// (warp w reads TMEM lanes 32*(w%4)..+31: one query per thread).  CG = 2 pairs two CTAs (SMs) on one
+// (warp w reads TMEM lanes 32*(w%4)..+31: one query per thread).  Producer and issuer run their loops warp-uniformly
+// and predicate the TMA / tcgen05 instructions on one elected lane (see elect_one_pred).  CG = 2 pairs two CTAs (SMs) on one
 // 256 x 256 tile with cta_group::2; see gemm_topk_kernel.
 #pragma once
 #include <cuda.h>
@@ -57,28 +58,11 @@ struct GemmParams {
 };
 
 // ---- PTX: TMA tensor load, tcgen05 ------------------------------------------------------------
-__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -157,14 +141,6 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// TMA load issued by either CTA of a pair; completion bytes are credited to the mbarrier of the
-// pair's leader (mbar is a shared::cluster address inside the leader CTA)
-__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst_smem), "l"(map), "r"(mbar), "r"(c0), "r"(c1)
-        : "memory");
-}
 template <int CG>
 __device__ __forceinline__ void tc_alloc_cg(uint32_t smem_dst, uint32_t ncols) {
     if (CG == 1) {
@@ -182,31 +158,6 @@ __device__ __forceinline__ void tc_dealloc_cg(uint32_t taddr, uint32_t ncols) {
     else
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-template <int CG>
-__device__ __forceinline__ void tc_mma_f16_cg(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (CG == 1) {
-        tc_mma_f16(d_tmem, adesc, bdesc, idesc, accumulate);
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
-    }
-}
-// arrive on `bar` when all prior MMAs retire; CG == 2: on the same barrier in both CTAs of the pair
-template <int CG>
-__device__ __forceinline__ void tc_commit_cg(uint32_t bar) {
-    if (CG == 1) {
-        tc_commit(bar);
-    } else {
-        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                     ::"r"(bar), "h"((uint16_t)3)
-                     : "memory");
-    }
-}
-
 // Warp-uniform issue.  Inside a divergent `if (lane == 0)` region ptxas has to move every operand of a tcgen05
 // instruction into uniform registers through an ELECT / R2UR waterfall (about 14 instructions and a loop per MMA —
 // measurable once an MMA takes 32 cycles).  Here every lane of the MMA warp runs the loop, the operands are computed
@@ -233,6 +184,8 @@ __device__ __forceinline__ void tma_load_2d_if(uint32_t elected, uint32_t dst_sm
         ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(bar), "r"(elected)
         : "memory");
 }
+// TMA load issued by either CTA of a pair; completion bytes are credited to the mbarrier of the pair's leader
+// (mbar is a shared::cluster address inside the leader CTA)
 __device__ __forceinline__ void tma_load_2d_cg2_if(uint32_t elected, uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, uint32_t mbar) {
     asm volatile(
         "{\n\t.reg .pred e;\n\t"
@@ -899,17 +852,16 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
         float acc = 0.0f;
         // lanes >= lpr stay at +0: adding them in the 32-lane butterfly below is exact, so the result
         // equals the lpr-lane butterfly of the scan kernel
-        for (uint32_t ch = lane; ch < p.nvec && lane < p.lpr; ch += p.lpr) {
-            uint4 raw = ldg_nc_v4(rp + (size_t)ch * 16);
-            auto step = [&](uint32_t bits, float qv) {  // same element arithmetic as scan_topk.cuh acc1<>
-                const float v = __uint_as_float(bits);
-                if (METRIC == 0) {
-                    acc = fmaf(v, qv, acc);
-                } else {
-                    const float t = v - qv;
-                    acc = fmaf(t, t, acc);
-                }
-            };
+        auto step = [&](uint32_t bits, float qv) {  // same element arithmetic as scan_topk.cuh acc1<>
+            const float v = __uint_as_float(bits);
+            if (METRIC == 0) {
+                acc = fmaf(v, qv, acc);
+            } else {
+                const float t = v - qv;
+                acc = fmaf(t, t, acc);
+            }
+        };
+        auto chunk = [&](const uint4& raw, uint32_t ch) {
             if (p.store == 0) {
                 float4 qv = q4[ch];
                 step(raw.x, qv.x); step(raw.y, qv.y); step(raw.z, qv.z); step(raw.w, qv.w);
@@ -919,6 +871,23 @@ __global__ void __launch_bounds__(256) rerank_kernel(const RerankParams p) {
                 step(raw.y << 16, qa.z); step(raw.y & 0xffff0000u, qa.w);
                 step(raw.z << 16, qb.x); step(raw.z & 0xffff0000u, qb.y);
                 step(raw.w << 16, qb.z); step(raw.w & 0xffff0000u, qb.w);
+            }
+        };
+        if (lane < p.lpr) {
+            // up to eight 16-byte loads of the row in flight per lane before the first is used (a candidate row is a
+            // random 3 KB read: latency, not arithmetic, bounds this kernel); the sums keep the scan's order
+            for (uint32_t base = lane; base < p.nvec; base += 8 * p.lpr) {
+                uint4 raw[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t ch = base + u * p.lpr;
+                    if (ch < p.nvec) raw[u] = ldg_nc_v4(rp + (size_t)ch * 16);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t ch = base + u * p.lpr;
+                    if (ch < p.nvec) chunk(raw[u], ch);
+                }
             }
         }
         acc = warp_sum_xor(acc);

@@ -37,7 +37,7 @@ def main():
     idx.add_synthetic(a.rows, 1234)
     q1 = torch.from_numpy(oracle.synth_rows(1, a.d, 99)).cuda()
     scan_ms, _ = timed(idx, q1, a.k)
-    shadow_gb = a.rows * (a.d + (2 if a.metric else 0) + 63) // 64 * 64 * 2 / 1e9
+    shadow_gb = a.rows * ((a.d + (2 if a.metric else 0) + 63) // 64 * 64) * 2 / 1e9
     for nq in (2, 4, 8, 16, 32, 64, 96, 128, 192, 256):
         q = torch.from_numpy(oracle.synth_rows(nq, a.d, 5678)).cuda()
         out = {"rows": a.rows, "d": a.d, "metric": "l2" if a.metric else "ip", "k": a.k, "nq": nq, "single_query_scan_ms": round(scan_ms, 3)}
