@@ -700,6 +700,8 @@ def main_b200(a):
     others = []
     if not a.no_others and a.workload == DEFAULT_WORKLOAD:
         for w in OTHER_CONFIGS + ([PREFILTER_WORKLOAD] if env.world == 1 else []):
+            if env.world > 1 and WORKLOADS[w][0] < 1_000_000:
+                continue  # config 0 (10k rows) is the CPU-runnable case: one GPU; sharding 10k rows measures nothing
             nq = WORKLOADS[w][6]
             st = max(5, min(a.steps, 10)) if nq == 1 else 5
             try:
