@@ -579,6 +579,10 @@ def run_workload(env: Env, a, workload: str, steps: int, warmup: int, *, headlin
     env.barrier()
     e2e_total, = env.max_over_ranks([time.perf_counter() - t_start])
     e2e_qps = steps * nq / e2e_total
+    # per rank: a sharded host batch uploads 1/world of the queries and all-gathers the rest over NVLink (sharded.py)
+    h2d_bytes = nq * d * 4
+    if world > 1 and h2d_bytes >= idx.query_allgather_min_bytes:
+        h2d_bytes = -(-nq // world) * d * 4
 
     # ---- parity: the oracle re-derives the last answers of the device-resident path (and the host path agrees) ----
     chk_steps = [total_steps - 1 - j for j in range(min(3, steps))] if nq == 1 else [total_steps - 1]
@@ -634,7 +638,7 @@ def run_workload(env: Env, a, workload: str, steps: int, warmup: int, *, headlin
                                  "overlap their tails by design); isolated_launch_ms = events around one search alone",
                          "avg_launch_ms": launch_ms, "isolated_launch_ms": iso_p50 / scans_per_step, "peak_source": peak_src,
                          "whole_job_gbs": bytes_per_scan_total * scans_per_step / (total_ms / steps * 1e-3) / 1e9},
-            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * k * 12,
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": nq * k * 12,
                     "p50_ms": 1e3 * statistics.median(e2e_lat), "max_ms": 1e3 * max(e2e_lat),
                     "timing": "host wall clock around index.search(numpy)"},
             "gpu_launches": int(launches),

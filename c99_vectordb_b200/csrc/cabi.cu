@@ -2016,13 +2016,17 @@ static int search_gemm(b200_index* ix, const float* q_dev, int64_t nq, int64_t k
             ix->stat_gemm_pass2_us = s_p2;
             ix->stat_gemm_rerank_us = s_rr;
         }
+        cudaError_t ce = cudaSuccess;
         if (rc == 0)
-            for (size_t j = 0; j < nb; ++j) {
-                cudaMemcpyAsync(D_dev + (size_t)bad[j] * k, Dtmp + j * k, (size_t)k * 4, cudaMemcpyDeviceToDevice, st);
-                cudaMemcpyAsync(I_dev + (size_t)bad[j] * k, Itmp + j * k, (size_t)k * 8, cudaMemcpyDeviceToDevice, st);
+            for (size_t j = 0; j < nb && ce == cudaSuccess; ++j) {
+                ce = cudaMemcpyAsync(D_dev + (size_t)bad[j] * k, Dtmp + j * k, (size_t)k * 4, cudaMemcpyDeviceToDevice, st);
+                if (ce == cudaSuccess)
+                    ce = cudaMemcpyAsync(I_dev + (size_t)bad[j] * k, Itmp + j * k, (size_t)k * 8, cudaMemcpyDeviceToDevice, st);
             }
-        cudaStreamSynchronize(st);  // the temporaries are released when this scope ends
+        const cudaError_t se = cudaStreamSynchronize(st);  // always: the temporaries are released when this scope ends
         if (rc) return rc;
+        CK(ce);
+        CK(se);
     }
     return 0;
 }

@@ -70,6 +70,9 @@ class ShardedIndexFlat:
         self._host_stage = {}
         self.last_batch_uncertified = None
         self.last_batch_stats = None
+        # host batches of at least this many bytes: every rank uploads 1/world of the queries and the rest arrives by
+        # an all-gather over NVLink (all ranks hold the same host queries; the PCIe links are the narrow part)
+        self.query_allgather_min_bytes = 1 << 20
 
     # ---- add --------------------------------------------------------------------------------
     def add_with_ids(self, x: np.ndarray, ids: np.ndarray) -> None:
@@ -306,8 +309,14 @@ class ShardedIndexFlat:
 
         x = np.ascontiguousarray(x, dtype=np.float32)
         assert x.ndim == 2 and x.shape[1] == self.d
-        if self.device.type != "cuda":
-            D, I = self.search_device(torch.from_numpy(x), k)
+        if self.device.type != "cuda":  # injected test index (gloo): same query exchange, no pinned staging
+            if self.world > 1 and x.nbytes >= self.query_allgather_min_bytes:
+                up = -(-x.shape[0] // self.world)
+                q = self._upload_queries(x, torch.empty((up, self.d), dtype=torch.float32),
+                                         torch.empty((up * self.world, self.d), dtype=torch.float32), True).contiguous()
+            else:
+                q = torch.from_numpy(x)
+            D, I = self.search_device(q, k)
             return D.numpy().copy(), I.numpy().copy()
         if self._fused_ok(x.shape[0], int(k)):
             # latency path: ONE C call — pinned staging, H2D, the fused kernel (its last CTA writes the merged result
@@ -318,23 +327,45 @@ class ShardedIndexFlat:
             _cabi.check(_cabi.load().b200_index_search_exchange(self.local.index._h, x.ctypes.data, x.shape[0], int(k),
                                                                 D.ctypes.data, I.ctypes.data))
             return D, I
-        key = (x.shape[0], int(k))
+        nq, k = x.shape[0], int(k)
+        gather = self.world > 1 and x.nbytes >= self.query_allgather_min_bytes
+        key = (nq, k, gather)
         st = self._host_stage.get(key)
         if st is None:
-            st = (torch.empty((x.shape[0], self.d), dtype=torch.float32).pin_memory(),
-                  torch.empty((x.shape[0], self.d), dtype=torch.float32, device=self.device),
-                  torch.empty((x.shape[0], int(k)), dtype=torch.float32).pin_memory(),
-                  torch.empty((x.shape[0], int(k)), dtype=torch.int64).pin_memory())
+            up = -(-nq // self.world) if gather else nq  # query rows this rank uploads
+            st = (torch.empty((up, self.d), dtype=torch.float32).pin_memory(),
+                  torch.empty((up * self.world if gather else nq, self.d), dtype=torch.float32, device=self.device),
+                  torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                  torch.empty((nq, k), dtype=torch.int64).pin_memory())
             self._host_stage[key] = st
         hq, dq, hD, hI = st
-        hq.numpy()[...] = x
-        dq.copy_(hq, non_blocking=True)
+        dq = self._upload_queries(x, hq, dq, gather)
         D, I = self.search_device(dq, k)
         hD.copy_(D, non_blocking=True)
         hI.copy_(I, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         self.check_exchange()
         return hD.numpy().copy(), hI.numpy().copy()
+
+    def _upload_queries(self, x: np.ndarray, hq, dq, gather: bool):
+        """Host queries -> dq on this rank's device.  gather: this rank stages and uploads only rows
+        [rank * up, (rank + 1) * up) (zero padded past nq) and one all-gather completes dq on every rank."""
+        import torch.distributed as dist
+
+        nq = x.shape[0]
+        if not gather:
+            hq.numpy()[...] = x
+            dq.copy_(hq, non_blocking=True)
+            return dq
+        up = hq.shape[0]
+        lo, hi = min(nq, self.rank * up), min(nq, (self.rank + 1) * up)
+        h = hq.numpy()
+        h[: hi - lo] = x[lo:hi]
+        h[hi - lo:] = 0.0
+        mine = dq[self.rank * up: (self.rank + 1) * up]
+        mine.copy_(hq, non_blocking=True)
+        dist.all_gather_into_tensor(dq, mine, group=self.group)
+        return dq[:nq]
 
     # ---- pieces -----------------------------------------------------------------------------
     def _local_search(self, q, k, D_loc, I_loc) -> None:

@@ -157,6 +157,38 @@ def test_sharded_search_equals_unsharded(tmp_path, world, metric, n, k, nq):
         np.testing.assert_array_equal(o, outs[0])  # every rank holds the merged answer
 
 
+def _query_exchange_worker(rank, world, port, metric, n, d, k, nq, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        db = oracle.synth_rows(n, d, 9)
+        ids = np.arange(n, dtype=np.int64)
+        q = oracle.synth_rows(nq, d, 8)
+        idx = ShardedIndexFlat(d, metric, local_index=OracleLocalIndex(d, metric), merge_fn=oracle.merge_topk, device="cpu")
+        idx.query_allgather_min_bytes = 0  # every host batch: upload 1/world of the queries, all-gather the rest
+        idx.add_with_ids(db, ids)
+        # this rank may only look at ITS slice of the host queries: everything else is poisoned here and must arrive
+        # from the rank that owns it
+        up = -(-nq // world)
+        mine = q.copy()
+        mine[: rank * up] = np.nan
+        mine[(rank + 1) * up:] = np.nan
+        D, I = idx.search(mine, k)
+        Dw, Iw = oracle.search(metric, db, q, k, ids=ids)
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nq", [(2, 7), (3, 5), (2, 1), (3, 2)])
+def test_host_batches_upload_one_slice_per_rank(tmp_path, world, nq):
+    """Host batches: each rank stages and uploads rows [rank * ceil(nq / world), ...) of the queries only, one
+    all-gather completes them everywhere (ragged and empty slices included)."""
+    mp.spawn(_query_exchange_worker, args=(world, _free_port(), 0, 500, 24, 6, nq, str(tmp_path)), nprocs=world, join=True)
+
+
 def test_shard_range_covers_rows_once():
     for n in (0, 1, 7, 8, 9, 100_000_000):
         for w in (1, 2, 3, 4, 8):
