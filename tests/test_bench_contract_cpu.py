@@ -29,3 +29,15 @@ def test_reference_arm_non_zero_ranks_exit_quietly():
 def test_scan_passes_mirror_query_blocking():
     assert [bench.scan_passes(n) for n in (1, 2, 3, 4, 5, 8, 9, 13, 100)] == [1, 1, 1, 1, 2, 1, 2, 3, 13]
     assert bench.DEFAULT_WORKLOAD in bench.WORKLOADS and bench.WORKLOADS[bench.DEFAULT_WORKLOAD][:2] == (10_000_000, 768)
+
+
+def test_l2_policy_says_what_fits():
+    """The `config.l2_policy` string has to say which case a workload is in (timing rules of the bench contract)."""
+    assert "no flush needed" in bench.l2_policy(bench.DEFAULT_WORKLOAD, 1) and ">> 126 MB" in bench.l2_policy(bench.DEFAULT_WORKLOAD, 8)
+    small = bench.l2_policy("10kx384_ip_f32_k10_nq100", 1)
+    assert "fits the 126 MB L2" in small and "no bandwidth claim" in small
+    mid = bench.l2_policy("1Mx768_cos_f32_k10_nq1", 8)  # 384 MB shard: larger than L2, streamed front to back
+    assert "> 126 MB L2" in mid and "fits" not in mid
+    assert bench.workload_config(bench.DEFAULT_WORKLOAD, 2)["l2_policy"] == bench.l2_policy(bench.DEFAULT_WORKLOAD, 2)
+    # config 0 is the CPU-runnable case: part of the one-GPU line only
+    assert bench.OTHER_CONFIGS[0] == "10kx384_ip_f32_k10_nq100" and bench.WORKLOADS[bench.OTHER_CONFIGS[0]][0] < 1_000_000
